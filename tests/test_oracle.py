@@ -1,0 +1,102 @@
+"""Pin the CPU oracle (oracle/) against the reference's own outputs
+(tests/golden, produced by tests/golden/make_golden.py from komb2_ref /
+CoreA.h) and against independent implementations (networkx, scipy)."""
+import networkx as nx
+import numpy as np
+import pytest
+import scipy.stats
+
+from conftest import (corea_case_names, komb2_case_names, load_corea_case,
+                      load_komb2_case)
+from komb_b200 import synth
+
+
+@pytest.mark.parametrize("name", komb2_case_names())
+def test_oracle_matches_reference_komb2(oracle_mod, name):
+    sam1, sam2, exp = load_komb2_case(name)
+    got = oracle_mod.komb2_expected(sam1, sam2, threads=exp["threads"])
+    assert got["edges"] == exp["edges"]                       # edge set bit-exact by Name
+    assert got["kcore"] == exp["kcore"]                       # Name -> (coreness, degree)
+    for nm, txt in exp["score_text"].items():                 # %f text: 6 decimals
+        assert abs(got["score"][nm] - float(txt)) <= 5.0e-7 + 1e-12
+
+
+def test_q1_line_drop_is_modelled(oracle_mod):
+    """-t 4 on the same input loses lines (graph.cpp:206-220); -t 1 does not."""
+    sam1, sam2, exp = load_komb2_case("mid_s3_t4")
+    t1 = oracle_mod.komb2_expected(sam1, sam2, threads=1)
+    assert exp["edges"] < t1["edges"]
+
+
+@pytest.mark.parametrize("name", corea_case_names())
+def test_oracle_corea_matches_reference_header(oracle_mod, name):
+    core, deg, ref = load_corea_case(name)
+    got = oracle_mod.corea(core, deg, oracle_mod.KEY_REF32)
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-12)
+    # ranks are exact half-integers: the only slack is libm log (<= 1 ulp each)
+    assert np.max(np.abs(got - ref)) < 1e-13
+
+
+def test_oracle_corea_overflow_modes_differ(oracle_mod):
+    core, deg, ref = load_corea_case("overflow_q5_n40000")
+    exact = oracle_mod.corea(core, deg, oracle_mod.KEY_EXACT64)
+    assert np.max(np.abs(exact - ref)) > 1.0      # quirk Q5: the reference wraps int32
+
+
+def test_oracle_ranks_equal_scipy(oracle_mod):
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 50, 5000).astype(np.int32)
+    core = np.minimum(deg, rng.integers(0, 9, 5000)).astype(np.int32)
+    rd, rk = oracle_mod.corea_ranks(core, deg, oracle_mod.KEY_EXACT64)
+    key = core.astype(np.int64) * 5000 + deg
+    assert np.array_equal(rd, scipy.stats.rankdata(-deg.astype(np.int64), "average"))
+    assert np.array_equal(rk, scipy.stats.rankdata(-key, "average"))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_coreness_equals_networkx(oracle_mod, seed):
+    u, v = synth.rmat_edges(10, 12000, n_vertices=900, seed=seed)
+    edges = oracle_mod.simplify(u, v)
+    deg, core = oracle_mod.coreness(900, edges)
+    eu, ev = oracle_mod.unpack_edges(edges)
+    g = nx.Graph()
+    g.add_nodes_from(range(900))
+    g.add_edges_from(zip(eu.tolist(), ev.tolist()))
+    cn = nx.core_number(g)
+    assert [cn[i] for i in range(900)] == core.tolist()
+    assert [g.degree(i) for i in range(900)] == deg.tolist()
+
+
+def test_oracle_kats(oracle_mod):
+    def core_of(n, pairs):
+        u = np.array([p[0] for p in pairs], np.uint32)
+        v = np.array([p[1] for p in pairs], np.uint32)
+        return oracle_mod.coreness(n, oracle_mod.simplify(u, v))[1].tolist()
+    k6 = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+    assert core_of(6, k6) == [5] * 6                                   # K_k -> k-1
+    assert core_of(5, [(i, i + 1) for i in range(4)]) == [1] * 5       # path
+    assert core_of(6, [(0, i) for i in range(1, 6)]) == [1] * 6        # star
+    assert core_of(5, [(i, (i + 1) % 5) for i in range(5)]) == [2] * 5  # ring
+    assert core_of(8, k6 + [(6, 7)] ) == [5] * 6 + [1, 1]              # disjoint
+    assert core_of(3, [(0, 1), (1, 0), (0, 0), (0, 1)]) == [1, 1, 0]   # dup, loop, isolated
+
+
+def test_oracle_ramp_has_many_levels(oracle_mod):
+    u, v = synth.ramp_edges(levels=40, per_level=8)
+    n = 40 * 8
+    deg, core = oracle_mod.coreness(n, oracle_mod.simplify(u, v))
+    assert core.max() >= 40
+    # the closing clique swallows the last (levels+1)/per_level levels; all others are present
+    assert set(range(1, 40 - 41 // 8)) <= set(core.tolist())
+
+
+def test_build_edges_semantics(oracle_mod):
+    # read 0: mate1 {5, 3}, mate2 {3, 9} -> set {3,5,9}; read 1: {7}; read 2 (mate2 only): {1, 2}
+    rk = np.array([0, 0, 1, 0, 0, 2, 2, 2], np.uint32)
+    ut = np.array([5, 3, 7, 3, 9, 1, 2, 1], np.uint32)
+    edges, P, S = oracle_mod.build_edges(rk, ut)
+    eu, ev = oracle_mod.unpack_edges(edges)
+    assert list(zip(eu.tolist(), ev.tolist())) == [(1, 2), (3, 5), (3, 9), (5, 9)]
+    assert (P, S) == (4, 6)
+    e0, p0, s0 = oracle_mod.build_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    assert e0.shape[0] == 0 and p0 == 0 and s0 == 0
