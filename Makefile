@@ -1,0 +1,34 @@
+# Build of the B200-native KOMB hot path (sm_100a only).
+#   make            -> komb_b200/libkombgpu.so  (CUDA kernels + C ABI), bin/komb2 (drop-in host)
+#   make oracle     -> oracle/libkomb_oracle.so (+ oracle/_ref when /root/reference exists): checkers only
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Ikomb_b200/csrc
+CSRC      := komb_b200/csrc
+OBJDIR    := build/obj
+CU        := $(CSRC)/capi.cu $(CSRC)/build.cu $(CSRC)/sort.cu $(CSRC)/peel.cu $(CSRC)/corea.cu
+OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU))
+HDR       := include/kombgpu.h $(wildcard $(CSRC)/*.cuh)
+
+all: komb_b200/libkombgpu.so bin/komb2
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) $(PTXAS_V) -c $< -o $@
+
+komb_b200/libkombgpu.so: $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart static
+
+bin/komb2: host/komb2.cpp host/sam_tokenizer.hpp host/cli.hpp include/kombgpu.h komb_b200/libkombgpu.so
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Iinclude host/komb2.cpp -o $@ -Lkomb_b200 -lkombgpu -Wl,-rpath,'$$ORIGIN/../komb_b200'
+
+oracle:
+	$(MAKE) -C oracle all
+	@if [ -f /root/reference/src/graph.cpp ]; then $(MAKE) -C oracle ref; fi
+
+clean:
+	rm -rf build komb_b200/libkombgpu.so bin
+
+.PHONY: all oracle clean

@@ -1,0 +1,169 @@
+/*
+ * kombgpu.h — C ABI of the B200-native KOMB hot path
+ *             (hits -> unitig adjacency graph -> k-core -> CORE-A).
+ *
+ * The reference (treangenlab/komb, komb2) has no FFI: its hot path is reached
+ * through the C++ methods of komb::Kgraph (src/graph.h:49-62) called in a fixed
+ * order from main (src/komb2.cpp:93-132).  This header is the boundary a
+ * maintainer binds instead: it starts where the reference
+ * holds tokenised hits (after src/graph.cpp:221-235) and ends where it formats
+ * its three output files (src/graph.cpp:423-426,467-475; CombineCoreA.h:36-39).
+ *
+ * Conventions
+ *   - every function returns 0 (KOMBGPU_OK) or a negative KOMBGPU_E* code;
+ *     nothing throws or exits across the ABI; kombgpu_last_error() gives text.
+ *   - plain pointers + sizes only.  Pointers are HOST pointers unless the
+ *     function name ends in `_dev` (then they are device pointers on the
+ *     context's device, e.g. a torch tensor's data_ptr()).
+ *   - the caller owns every buffer it passes; the library owns device memory
+ *     behind the opaque handles.  One context per process and device; calls on
+ *     one context are serialised by the caller.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with KOMBGPU_ENODEV.
+ */
+#ifndef KOMBGPU_H
+#define KOMBGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KOMBGPU_ABI_VERSION 1
+
+enum {
+    KOMBGPU_OK = 0,
+    KOMBGPU_EINVAL = -1,  /* bad argument (null pointer, id out of range, ...)   */
+    KOMBGPU_ENODEV = -2,  /* no usable CUDA device / device is not sm_100        */
+    KOMBGPU_ENOMEM = -3,  /* device or host allocation failed                    */
+    KOMBGPU_ECUDA = -4,   /* a CUDA call or kernel failed (see last_error)       */
+    KOMBGPU_ESTATE = -5,  /* call order violated (e.g. corea before coreness)    */
+    KOMBGPU_EINTERNAL = -6 /* internal invariant broken (peel watchdog tripped)  */
+};
+
+/* CORE-A key arithmetic (reference src/CoreA.h:122). */
+enum {
+    KOMBGPU_KEY_REF32 = 0,   /* (int32)(coreness * n + degree), wraps like the reference */
+    KOMBGPU_KEY_EXACT64 = 1  /* the same expression without overflow                     */
+};
+
+typedef struct kombgpu_ctx kombgpu_ctx;
+typedef struct kombgpu_graph kombgpu_graph;
+
+/* Sizes and device timings of the last operations on a graph. */
+typedef struct kombgpu_stats {
+    uint64_t n_hits;         /* H: hits passed to build_graph                          */
+    uint64_t n_unique_hits;  /* distinct (read, unitig)                                */
+    uint64_t n_pairs;        /* P: clique pairs emitted before dedup (or m for from_edges) */
+    uint64_t n_edges;        /* E: simple undirected edges                             */
+    uint32_t n_vertices;     /* n                                                      */
+    int32_t max_degree;
+    int32_t max_coreness;    /* -1 until kombgpu_coreness ran                          */
+    uint32_t peel_levels;    /* non-empty coreness levels processed                    */
+    uint32_t peel_rounds;    /* grid-wide dependent rounds (scan+process phases)       */
+    float ms_build;          /* CUDA-event time: hits/edges -> CSR                     */
+    float ms_peel;           /* CUDA-event time: k-core peel                           */
+    float ms_corea;          /* CUDA-event time: CORE-A                                */
+    uint64_t kernel_launches; /* kernels of this library launched for this graph       */
+} kombgpu_stats;
+
+/* ---- context ------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device` (a CUDA ordinal).  Replaces the
+ * reference's `komb::Kgraph(threads, readlen)` constructor (src/graph.cpp:52-56,
+ * src/komb2.cpp:79) as the per-process state holder. */
+int kombgpu_ctx_create(int device, kombgpu_ctx **out);
+void kombgpu_ctx_destroy(kombgpu_ctx *ctx);
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t cast
+ * to void*, e.g. torch.cuda.current_stream().cuda_stream).  NULL restores the
+ * context's own stream. */
+int kombgpu_ctx_set_stream(kombgpu_ctx *ctx, void *cuda_stream);
+
+/* Text of the last error on this context (never NULL).  With ctx == NULL:
+ * the last error of a failed kombgpu_ctx_create on this thread. */
+const char *kombgpu_last_error(const kombgpu_ctx *ctx);
+
+/* Release cached device workspace held by the context. */
+int kombgpu_ctx_trim(kombgpu_ctx *ctx);
+
+/* ---- stage 1: graph build ------------------------------------------------- */
+
+/* Hits of BOTH mate files, concatenated: hit i = read `read_key[i]` aligned to
+ * unitig `unitig[i]` (< n_vertices).  Builds the simple undirected unitig graph:
+ * per-read union of unitig sets, every set a clique, duplicates and loops
+ * dropped.  Replaces Kgraph::getEdgeInfo + generateGraph + igraph_create +
+ * igraph_simplify (src/graph.cpp:259-285, 287-393, 418, 438). */
+int kombgpu_build_graph(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig,
+                        uint64_t n_hits, uint32_t n_vertices, kombgpu_graph **out);
+int kombgpu_build_graph_dev(kombgpu_ctx *ctx, const uint32_t *read_key_dev, const uint32_t *unitig_dev,
+                            uint64_t n_hits, uint32_t n_vertices, kombgpu_graph **out);
+
+/* Arbitrary (u, v) pairs, ids < n_vertices; duplicates, both orientations and
+ * self-loops allowed.  Replaces igraph_create + igraph_simplify
+ * (src/graph.cpp:418, 438) for an edge list that already exists. */
+int kombgpu_graph_from_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v,
+                             uint64_t n_pairs, uint32_t n_vertices, kombgpu_graph **out);
+int kombgpu_graph_from_edges_dev(kombgpu_ctx *ctx, const uint32_t *u_dev, const uint32_t *v_dev,
+                                 uint64_t n_pairs, uint32_t n_vertices, kombgpu_graph **out);
+
+void kombgpu_graph_destroy(kombgpu_graph *g);
+
+/* |V| and |E| of the simple graph (igraph_vcount / igraph_ecount,
+ * src/graph.cpp:443-444). */
+int kombgpu_graph_counts(const kombgpu_graph *g, uint32_t *n_vertices, uint64_t *n_edges);
+
+/* Canonical edge list: u[i] < v[i], ascending by (u, v); each array holds
+ * n_edges entries.  This is what the drop-in writes to edgelist.txt (quirk Q7). */
+int kombgpu_graph_edges(const kombgpu_graph *g, uint32_t *u, uint32_t *v);
+
+/* CSR of the symmetric graph: row_ptr[n+1], col[2E], every row ascending. */
+int kombgpu_graph_csr(const kombgpu_graph *g, uint64_t *row_ptr, uint32_t *col);
+
+/* ---- stage 2: degree + coreness ------------------------------------------- */
+
+/* igraph_degree(ALL, NO_LOOPS) (src/graph.cpp:462): degree[n]. */
+int kombgpu_degree(const kombgpu_graph *g, int32_t *degree);
+
+/* igraph_coreness(ALL) (src/graph.cpp:463): runs the frontier peel on first
+ * call, then copies coreness[n] to the host (coreness may be NULL to only run). */
+int kombgpu_coreness(kombgpu_graph *g, int32_t *coreness);
+
+/* ---- stage 3: CORE-A ------------------------------------------------------- */
+
+/* CoreA::getAnomalyScore (src/CoreA.h:109-140) on host arrays:
+ * score[i] = |ln rank(degree)[i] - ln rank(key)[i]|, descending average-tie
+ * ranks (src/CoreA.h:142-187). */
+int kombgpu_corea(kombgpu_ctx *ctx, const int32_t *coreness, const int32_t *degree,
+                  uint32_t n, int key_mode, double *score);
+
+/* The same on the device-resident coreness/degree of a graph (requires
+ * kombgpu_coreness first).  score may be NULL to only run. */
+int kombgpu_graph_corea(kombgpu_graph *g, int key_mode, double *score);
+
+/* The two scalars CombineCoreA::run prints (src/CombineCoreA.h:24-25,31-32):
+ * max coreness (dense ratio = max_coreness / 2, integer division) and the max
+ * CORE-A score. */
+int kombgpu_graph_summary(const kombgpu_graph *g, int32_t *max_coreness, double *max_score);
+
+/* ---- whole path + introspection --------------------------------------------- */
+
+/* build (already done) -> coreness -> CORE-A in one call, results left on the
+ * device; the three getters above then only copy. */
+int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode);
+
+int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out);
+
+/* Device pointers of the graph's arrays (valid until kombgpu_graph_destroy);
+ * any out-pointer may be NULL.  coreness/score are NULL until computed. */
+int kombgpu_graph_device_arrays(const kombgpu_graph *g, const uint64_t **row_ptr, const uint32_t **col,
+                                const uint64_t **edges_packed, const int32_t **degree,
+                                const int32_t **coreness, const double **score);
+
+int kombgpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOMBGPU_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of komb_b200/libkombgpu.so (the C ABI in include/kombgpu.h).
+
+There is no fallback of any kind: if the shared library is missing, or no B200
+is visible when a context is created, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_uint32, c_uint64, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libkombgpu.so"
+
+OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE, EINTERNAL = 0, -1, -2, -3, -4, -5, -6
+KEY_REF32, KEY_EXACT64 = 0, 1
+ERROR_NAMES = {EINVAL: "KOMBGPU_EINVAL", ENODEV: "KOMBGPU_ENODEV", ENOMEM: "KOMBGPU_ENOMEM",
+               ECUDA: "KOMBGPU_ECUDA", ESTATE: "KOMBGPU_ESTATE", EINTERNAL: "KOMBGPU_EINTERNAL"}
+
+
+class Stats(ctypes.Structure):
+    """struct kombgpu_stats"""
+    _fields_ = [
+        ("n_hits", c_uint64), ("n_unique_hits", c_uint64), ("n_pairs", c_uint64), ("n_edges", c_uint64),
+        ("n_vertices", c_uint32), ("max_degree", c_int32), ("max_coreness", c_int32),
+        ("peel_levels", c_uint32), ("peel_rounds", c_uint32),
+        ("ms_build", c_float), ("ms_peel", c_float), ("ms_corea", c_float),
+        ("kernel_launches", c_uint64),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/kombgpu.h declares: name -> (restype, argtypes)
+u32p, u64p, i32p, f64p = POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32), POINTER(c_double)
+SIGNATURES = {
+    "kombgpu_abi_version": (c_int, []),
+    "kombgpu_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "kombgpu_ctx_destroy": (None, [c_void_p]),
+    "kombgpu_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
+    "kombgpu_last_error": (c_char_p, [c_void_p]),
+    "kombgpu_ctx_trim": (c_int, [c_void_p]),
+    "kombgpu_build_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_build_graph_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_graph_from_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_graph_from_edges_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_graph_destroy": (None, [c_void_p]),
+    "kombgpu_graph_counts": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64)]),
+    "kombgpu_graph_edges": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kombgpu_graph_csr": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kombgpu_degree": (c_int, [c_void_p, c_void_p]),
+    "kombgpu_coreness": (c_int, [c_void_p, c_void_p]),
+    "kombgpu_corea": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p]),
+    "kombgpu_graph_corea": (c_int, [c_void_p, c_int, c_void_p]),
+    "kombgpu_graph_summary": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_double)]),
+    "kombgpu_graph_analyse": (c_int, [c_void_p, c_int]),
+    "kombgpu_graph_stats": (c_int, [c_void_p, POINTER(Stats)]),
+    "kombgpu_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
+}
+
+_lib = None
+
+
+class KombGpuError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load libkombgpu.so and bind every declared symbol (no CUDA call is made)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built. Run `make` (or "
+                "`python -c 'import __graft_entry__ as e; e.build()'`). There is no CPU fallback.")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.kombgpu_abi_version() != 1:
+            raise RuntimeError("libkombgpu.so ABI version mismatch")
+        _lib = lib
+    return _lib

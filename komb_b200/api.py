@@ -1,0 +1,190 @@
+"""Host-side Python face of the KOMB hot path, a thin mirror of the C ABI
+(include/kombgpu.h) used by the tests and by bench.py.
+
+The call order is the reference's (src/komb2.cpp:93-132):
+    readSAM x2 + getEdgeInfo + generateGraph + igraph_create/simplify -> Context.build_graph
+    runCore (igraph_degree, igraph_coreness)                         -> Graph.degree / Graph.coreness
+    anomalyDetection -> CombineCoreA::run -> CoreA::getAnomalyScore   -> Graph.corea
+
+Arrays may be numpy arrays (host pointers -> the plain entry points, copies
+included) or torch CUDA tensors (device pointers -> the `_dev` entry points).
+Everything is computed by the CUDA library; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int32, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import KEY_EXACT64, KEY_REF32, KombGpuError, Stats  # noqa: F401
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _host(x, dtype) -> np.ndarray:
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a
+
+
+def _ptr(a: np.ndarray) -> c_void_p:
+    return c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One per process and device (kombgpu_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = c_void_p()
+        rc = self._lib.kombgpu_ctx_create(int(device), byref(h))
+        if rc != 0:
+            raise KombGpuError(rc, self._lib.kombgpu_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kombgpu_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KombGpuError(rc, self._lib.kombgpu_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._lib.kombgpu_ctx_set_stream(self._h, c_void_p(cuda_stream or 0)))
+
+    def trim(self):
+        self._check(self._lib.kombgpu_ctx_trim(self._h))
+
+    def _pair_call(self, host_fn, dev_fn, a, b, n_vertices: int) -> "Graph":
+        g = c_void_p()
+        if _is_torch_cuda(a):
+            import torch
+            assert _is_torch_cuda(b) and a.dtype in (torch.uint32, torch.int32) and b.dtype == a.dtype
+            assert a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+            rc = dev_fn(self._h, c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), a.numel(), n_vertices, byref(g))
+            keep = (a, b)
+        else:
+            ha, hb = _host(a, np.uint32), _host(b, np.uint32)
+            if ha.shape != hb.shape or ha.ndim != 1:
+                raise ValueError("expected two 1-D arrays of equal length")
+            rc = host_fn(self._h, _ptr(ha), _ptr(hb), ha.shape[0], n_vertices, byref(g))
+            keep = None
+        self._check(rc)
+        return Graph(self, g, keep)
+
+    def build_graph(self, read_key, unitig, n_vertices: int) -> "Graph":
+        """Hits of both mate files (concatenated) -> simple unitig graph."""
+        return self._pair_call(self._lib.kombgpu_build_graph, self._lib.kombgpu_build_graph_dev,
+                               read_key, unitig, int(n_vertices))
+
+    def graph_from_edges(self, u, v, n_vertices: int) -> "Graph":
+        return self._pair_call(self._lib.kombgpu_graph_from_edges, self._lib.kombgpu_graph_from_edges_dev,
+                               u, v, int(n_vertices))
+
+    def corea(self, coreness, degree, key_mode: int = KEY_REF32) -> np.ndarray:
+        """CoreA::getAnomalyScore on host arrays."""
+        c, d = _host(coreness, np.int32), _host(degree, np.int32)
+        if c.shape != d.shape or c.ndim != 1:
+            raise ValueError("expected two 1-D arrays of equal length")
+        score = np.empty(c.shape[0], dtype=np.float64)
+        self._check(self._lib.kombgpu_corea(self._h, _ptr(c), _ptr(d), c.shape[0], int(key_mode), _ptr(score)))
+        return score
+
+
+class Graph:
+    """Device-resident simple unitig graph (kombgpu_graph)."""
+
+    def __init__(self, ctx: Context, handle: c_void_p, keepalive=None):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self._h = handle
+        self._keep = keepalive
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kombgpu_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def counts(self) -> tuple[int, int]:
+        n, m = c_uint32(), c_uint64()
+        self._ctx._check(self._lib.kombgpu_graph_counts(self._h, byref(n), byref(m)))
+        return n.value, m.value
+
+    def edges(self) -> tuple[np.ndarray, np.ndarray]:
+        _, m = self.counts()
+        u, v = np.empty(m, np.uint32), np.empty(m, np.uint32)
+        self._ctx._check(self._lib.kombgpu_graph_edges(self._h, _ptr(u), _ptr(v)))
+        return u, v
+
+    def csr(self) -> tuple[np.ndarray, np.ndarray]:
+        n, m = self.counts()
+        row_ptr, col = np.empty(n + 1, np.uint64), np.empty(2 * m, np.uint32)
+        self._ctx._check(self._lib.kombgpu_graph_csr(self._h, _ptr(row_ptr), _ptr(col)))
+        return row_ptr, col
+
+    def degree(self) -> np.ndarray:
+        n, _ = self.counts()
+        d = np.empty(n, np.int32)
+        self._ctx._check(self._lib.kombgpu_degree(self._h, _ptr(d)))
+        return d
+
+    def coreness(self, copy: bool = True):
+        n, _ = self.counts()
+        if not copy:
+            self._ctx._check(self._lib.kombgpu_coreness(self._h, None))
+            return None
+        c = np.empty(n, np.int32)
+        self._ctx._check(self._lib.kombgpu_coreness(self._h, _ptr(c)))
+        return c
+
+    def corea(self, key_mode: int = KEY_REF32, copy: bool = True):
+        n, _ = self.counts()
+        if not copy:
+            self._ctx._check(self._lib.kombgpu_graph_corea(self._h, int(key_mode), None))
+            return None
+        s = np.empty(n, np.float64)
+        self._ctx._check(self._lib.kombgpu_graph_corea(self._h, int(key_mode), _ptr(s)))
+        return s
+
+    def analyse(self, key_mode: int = KEY_REF32):
+        self._ctx._check(self._lib.kombgpu_graph_analyse(self._h, int(key_mode)))
+
+    def summary(self) -> tuple[int, float]:
+        mc, ms = c_int32(), c_double()
+        self._ctx._check(self._lib.kombgpu_graph_summary(self._h, byref(mc), byref(ms)))
+        return mc.value, ms.value
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._ctx._check(self._lib.kombgpu_graph_stats(self._h, byref(st)))
+        return st.as_dict()
+
+    def device_arrays(self) -> dict:
+        ptrs = [c_void_p() for _ in range(6)]
+        self._ctx._check(self._lib.kombgpu_graph_device_arrays(self._h, *[byref(p) for p in ptrs]))
+        names = ["row_ptr", "col", "edges_packed", "degree", "coreness", "score"]
+        return {k: (p.value or 0) for k, p in zip(names, ptrs)}

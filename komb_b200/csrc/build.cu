@@ -1,0 +1,408 @@
+// build.cu — stage 1 of the KOMB hot path on the device:
+//   hits (read_key, unitig)  ->  per-read unitig sets  ->  clique pairs
+//   ->  simple undirected edge set  ->  CSR of the symmetric graph.
+//
+// Restates, as sort/scan/compact kernels over integer arrays, what the reference
+// does with string-keyed hash maps:
+//   per-read set insert + mate union   src/graph.cpp:235,259-285   sort + adjacent-unique of (read, unitig)
+//   all i<j pairs of every set         src/graph.cpp:332-347       segment scan + load-balanced pair emission
+//   dedup / igraph_simplify            src/graph.cpp:342-347,438   sort + adjacent-unique of (min, max)
+//   igraph_create adjacency index      src/graph.cpp:418           boundary detection + scan -> CSR
+// No atomics are needed anywhere in this stage: every count falls out of run
+// boundaries in sorted arrays, so the result (including the order inside each
+// CSR row) is deterministic.
+#include "graph.cuh"
+#include "primitives.cuh"
+
+namespace kg {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline uint32_t grid_for(uint64_t n, int per_block) { return ceil_div_u64(n ? n : 1, per_block); }
+
+// ---- packing ---------------------------------------------------------------
+
+// key = read_key << 32 | unitig; also the max read key (for the sort plan) and an
+// out-of-range flag.  info[0] = max read key, info[1] = error flag.
+__global__ void __launch_bounds__(kThreads) pack_hits_kernel(const uint32_t *__restrict__ read_key,
+                                                             const uint32_t *__restrict__ unitig, uint64_t n_hits,
+                                                             uint32_t n_vertices, uint64_t *__restrict__ keys,
+                                                             uint32_t *__restrict__ info) {
+    uint32_t local_max = 0;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_hits; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r = read_key[i], u = unitig[i];
+        bad |= (u >= n_vertices);
+        local_max = max(local_max, r);
+        keys[i] = ((uint64_t)r << 32) | u;
+    }
+    local_max = warp_reduce_max(local_max);
+    if (lane_id() == 0 && local_max) atomicMax(&info[0], local_max);
+    if (__any_sync(kFullMask, bad) && lane_id() == 0) atomicOr(&info[1], 1u);
+}
+
+// canonical undirected key (min << 32 | max); loops keep u == v and are dropped
+// by the unique pass.
+__global__ void __launch_bounds__(kThreads) pack_pairs_kernel(const uint32_t *__restrict__ u, const uint32_t *__restrict__ v,
+                                                              uint64_t n_pairs, uint32_t n_vertices,
+                                                              uint64_t *__restrict__ keys, uint32_t *__restrict__ info) {
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t a = u[i], b = v[i];
+        bad |= (a >= n_vertices) | (b >= n_vertices);
+        uint32_t lo = min(a, b), hi = max(a, b);
+        keys[i] = ((uint64_t)lo << 32) | hi;
+    }
+    if (__any_sync(kFullMask, bad) && lane_id() == 0) atomicOr(&info[1], 1u);
+}
+
+// ---- per-read segments -------------------------------------------------------
+
+// A "good" segment is a read with >= 2 distinct unitigs.  hi word counts good
+// heads, lo word counts good tails; the s-th good head and the s-th good tail
+// delimit the s-th good segment.
+struct SegFlagIn {
+    const uint64_t *hits;  // sorted unique (read << 32 | unitig)
+    uint64_t n;
+    __device__ uint64_t operator()(uint64_t i) const {
+        uint32_t r = (uint32_t)(hits[i] >> 32);
+        bool same_prev = i > 0 && (uint32_t)(hits[i - 1] >> 32) == r;
+        bool same_next = i + 1 < n && (uint32_t)(hits[i + 1] >> 32) == r;
+        uint64_t head = (!same_prev && same_next) ? 1ull : 0ull;
+        uint64_t tail = (same_prev && !same_next) ? 1ull : 0ull;
+        return (head << 32) | tail;
+    }
+};
+struct SegFlagOut {
+    uint32_t *seg_head;
+    uint32_t *seg_tail;
+    __device__ void operator()(uint64_t i, uint64_t prefix, uint64_t v) const {
+        if (v >> 32) seg_head[prefix >> 32] = (uint32_t)i;
+        if (v & 0xffffffffu) seg_tail[prefix & 0xffffffffu] = (uint32_t)i;
+    }
+};
+
+// pairs of segment s = C(size, 2)
+struct SegPairsIn {
+    const uint32_t *seg_head;
+    const uint32_t *seg_tail;
+    __device__ uint64_t operator()(uint64_t s) const {
+        uint64_t k = (uint64_t)(seg_tail[s] - seg_head[s]) + 1;
+        return k * (k - 1) / 2;
+    }
+};
+struct SegPairsOut {
+    uint64_t *seg_base;
+    __device__ void operator()(uint64_t s, uint64_t prefix, uint64_t) const { seg_base[s] = prefix; }
+};
+
+// ---- load-balanced pair emission ----------------------------------------------
+
+constexpr int kEmitItems = 8;
+constexpr int kEmitTile = kThreads * kEmitItems;  // outputs per CTA
+
+// tile_seg[t] = last segment s with seg_base[s] <= t * kEmitTile
+__global__ void __launch_bounds__(kThreads) emit_partition_kernel(const uint64_t *__restrict__ seg_base, uint32_t n_seg,
+                                                                  uint32_t n_tiles, uint32_t *__restrict__ tile_seg) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint64_t p = (uint64_t)t * kEmitTile;
+    uint32_t lo = 0, hi = n_seg;  // invariant: seg_base[lo] <= p, (hi == n_seg or seg_base[hi] > p)
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (seg_base[mid] <= p) lo = mid; else hi = mid;
+    }
+    tile_seg[t] = lo;
+}
+
+__global__ void __launch_bounds__(kThreads) emit_pairs_kernel(const uint64_t *__restrict__ hits,
+                                                              const uint32_t *__restrict__ seg_head,
+                                                              const uint64_t *__restrict__ seg_base, uint32_t n_seg,
+                                                              const uint32_t *__restrict__ tile_seg, uint32_t n_tiles,
+                                                              uint64_t n_pairs, uint64_t *__restrict__ pairs) {
+    __shared__ uint64_t s_base[kEmitTile + 2];
+    __shared__ uint32_t s_head[kEmitTile + 2];
+    const uint32_t tile = blockIdx.x;
+    const uint64_t p0 = (uint64_t)tile * kEmitTile;
+    const uint64_t p1 = min(n_pairs, p0 + kEmitTile);
+    const uint32_t s_first = tile_seg[tile];
+    const uint32_t s_last = tile + 1 < n_tiles ? tile_seg[tile + 1] : n_seg - 1;
+    const uint32_t cnt = s_last - s_first + 1;  // <= kEmitTile + 1: every segment is non-empty
+    for (uint32_t i = threadIdx.x; i < cnt; i += kThreads) {
+        s_base[i] = seg_base[s_first + i];
+        s_head[i] = seg_head[s_first + i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kEmitItems; ++j) {
+        uint64_t p = p0 + (uint64_t)j * kThreads + threadIdx.x;
+        if (p >= p1) break;
+        uint32_t lo = 0, hi = cnt;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_base[mid] <= p) lo = mid; else hi = mid;
+        }
+        // t-th pair (a < b) of the segment in colexicographic order: t = b(b-1)/2 + a
+        uint64_t t = p - s_base[lo];
+        uint64_t b = (uint64_t)((1.0 + sqrt(1.0 + 8.0 * (double)t)) * 0.5);
+        while (b * (b - 1) / 2 > t) --b;
+        while ((b + 1) * b / 2 <= t) ++b;
+        uint64_t a = t - b * (b - 1) / 2;
+        const uint64_t h = s_head[lo];
+        uint32_t ua = (uint32_t)hits[h + a], ub = (uint32_t)hits[h + b];  // ua < ub: sorted unique within the read
+        pairs[p] = ((uint64_t)ua << 32) | ub;
+    }
+}
+
+// ---- unique of sorted pair keys, dropping loops ---------------------------------
+
+struct EdgeFlagIn {
+    const uint64_t *keys;
+    __device__ uint32_t operator()(uint64_t i) const {
+        uint64_t k = keys[i];
+        bool head = (i == 0 || keys[i - 1] != k);
+        bool loop = (uint32_t)(k >> 32) == (uint32_t)k;
+        return (head && !loop) ? 1u : 0u;
+    }
+};
+
+// ---- CSR ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads) swap_pack_kernel(const uint64_t *__restrict__ edges, uint64_t n_edges,
+                                                             uint64_t *__restrict__ swapped) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = edges[i];
+        swapped[i] = (e << 32) | (e >> 32);
+    }
+}
+
+// keys sorted by their high word x in [0, n): start[x] = first index whose high
+// word is >= x, for x in [0, n]  (start[n] = count).  No atomics: thread i fills
+// the ids between its predecessor's high word and its own.
+__global__ void __launch_bounds__(kThreads) row_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t count,
+                                                              uint32_t n, uint32_t *__restrict__ start) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t cur = i < count ? (int64_t)(keys[i] >> 32) : (int64_t)n;
+        int64_t prev = i > 0 ? (int64_t)(keys[i - 1] >> 32) : -1;
+        for (int64_t x = prev + 1; x <= cur; ++x) start[x] = (uint32_t)i;
+    }
+}
+
+struct DegreeIn {
+    const uint32_t *fwd_start;
+    const uint32_t *back_start;
+    __device__ uint64_t operator()(uint64_t v) const {
+        return (uint64_t)(fwd_start[v + 1] - fwd_start[v]) + (uint64_t)(back_start[v + 1] - back_start[v]);
+    }
+};
+struct DegreeOut {
+    uint64_t *row_ptr;
+    int32_t *deg;
+    __device__ void operator()(uint64_t v, uint64_t prefix, uint64_t d) const {
+        row_ptr[v] = prefix;
+        deg[v] = (int32_t)d;
+    }
+};
+
+// max of an int32 array: warp shuffle -> one atomic per warp
+__global__ void __launch_bounds__(kThreads) reduce_max_i32_kernel(const int32_t *__restrict__ x, uint64_t n,
+                                                                  int32_t *__restrict__ out) {
+    int32_t m = INT32_MIN;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, x[i]);
+    m = warp_reduce_max(m);
+    if (lane_id() == 0 && m != INT32_MIN) atomicMax(out, m);
+}
+
+// Row v = [back neighbours (< v, ascending) | forward neighbours (> v, ascending)].
+__global__ void __launch_bounds__(kThreads) fill_col_kernel(const uint64_t *__restrict__ edges,
+                                                            const uint64_t *__restrict__ swapped, uint64_t n_edges,
+                                                            const uint64_t *__restrict__ row_ptr,
+                                                            const uint32_t *__restrict__ fwd_start,
+                                                            const uint32_t *__restrict__ back_start,
+                                                            uint32_t *__restrict__ col) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = edges[i];
+        uint32_t u = (uint32_t)(e >> 32);
+        uint64_t nback = back_start[u + 1] - back_start[u];
+        col[row_ptr[u] + nback + (i - fwd_start[u])] = (uint32_t)e;
+        uint64_t s = swapped[i];
+        uint32_t v = (uint32_t)(s >> 32);
+        col[row_ptr[v] + (i - back_start[v])] = (uint32_t)s;
+    }
+}
+
+__global__ void set_u64_kernel(uint64_t *p, uint64_t v) { *p = v; }
+
+// sorted (loops possible) pair keys -> g->edges / CSR.  `keys` has `count` entries.
+int finish_graph(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, uint32_t n, kombgpu_graph *g) {
+    const int bn = bits_for(n > 0 ? n - 1 : 0);
+    // unique + loop drop
+    DevBuf<uint32_t> d_count(ctx, 1);
+    if (!d_count) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    DevBuf<uint64_t> edges;
+    KG_ALLOC(ctx, edges, count);
+    KG_TRY((device_scan<uint32_t>(ctx, count, EdgeFlagIn{keys}, CompactKeysU64{keys, edges.p}, d_count.p)));
+    uint32_t n_edges32 = 0;
+    KG_TRY(read_back(ctx, d_count.p, &n_edges32, 1));
+    const uint64_t E = n_edges32;
+    g->n = n;
+    g->n_edges = E;
+    g->st.n_edges = E;
+    g->st.n_vertices = n;
+
+    // backward half: (v << 32 | u) stably sorted by v
+    DevBuf<uint64_t> sw_a, sw_b;
+    KG_ALLOC(ctx, sw_a, E);
+    KG_ALLOC(ctx, sw_b, E);
+    uint64_t *swapped = sw_a.p;
+    if (E) {
+        KG_LAUNCH(ctx, swap_pack_kernel, min(grid_for(E, kThreads), 148u * 16u), kThreads, 0, edges.p, E, sw_a.p);
+        RadixPass passes[8];
+        int np = plan_radix_passes(32, 32 + bn, 0, 0, passes);
+        KG_TRY(radix_sort_u64(ctx, sw_a.p, sw_b.p, E, passes, np, &swapped));
+    }
+    DevBuf<uint32_t> fwd_start, back_start;
+    KG_ALLOC(ctx, fwd_start, (size_t)n + 1);
+    KG_ALLOC(ctx, back_start, (size_t)n + 1);
+    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, edges.p, E, n, fwd_start.p);
+    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, swapped, E, n, back_start.p);
+
+    DevBuf<uint64_t> row_ptr;
+    DevBuf<int32_t> deg, max_deg(ctx, 1);
+    DevBuf<uint32_t> col;
+    KG_ALLOC(ctx, row_ptr, (size_t)n + 1);
+    KG_ALLOC(ctx, deg, n);
+    KG_ALLOC(ctx, col, 2 * E);
+    if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
+    KG_TRY((device_scan<uint64_t>(ctx, n, DegreeIn{fwd_start.p, back_start.p}, DegreeOut{row_ptr.p, deg.p},
+                                  (uint64_t *)nullptr)));
+    if (n) KG_LAUNCH(ctx, reduce_max_i32_kernel, min(grid_for(n, kThreads), 148u * 8u), kThreads, 0, deg.p, (uint64_t)n, max_deg.p);
+    KG_LAUNCH(ctx, set_u64_kernel, 1, 1, 0, row_ptr.p + n, 2 * E);
+    if (E)
+        KG_LAUNCH(ctx, fill_col_kernel, min(grid_for(E, kThreads), 148u * 16u), kThreads, 0, edges.p, swapped, E, row_ptr.p,
+                  fwd_start.p, back_start.p, col.p);
+    KG_TRY(read_back(ctx, max_deg.p, &g->st.max_degree, 1));
+
+    g->edges = edges.take();
+    g->row_ptr = row_ptr.take();
+    g->col = col.take();
+    g->deg = deg.take();
+    return KOMBGPU_OK;
+}
+
+}  // namespace
+
+int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                     kombgpu_graph *g) {
+    if (n_pairs >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_pairs >= 2^32 is not supported on one device");
+    const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
+    DevBuf<uint64_t> ka, kb;
+    DevBuf<uint32_t> info(ctx, 2);
+    KG_ALLOC(ctx, ka, n_pairs);
+    KG_ALLOC(ctx, kb, n_pairs);
+    if (!info) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    uint64_t *sorted = ka.p;
+    if (n_pairs) {
+        KG_LAUNCH(ctx, pack_pairs_kernel, min(grid_for(n_pairs, kThreads), 148u * 16u), kThreads, 0, u, v, n_pairs, n_vertices,
+                  ka.p, info.p);
+        RadixPass passes[8];
+        int np = plan_radix_passes(0, bn, 32, 32 + bn, passes);
+        KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n_pairs, passes, np, &sorted));
+    }
+    uint32_t h_info[2] = {0, 0};
+    KG_TRY(read_back(ctx, info.p, h_info, 2));
+    if (h_info[1]) return ctx_fail(ctx, KOMBGPU_EINVAL, "edge endpoint >= n_vertices (%u)", n_vertices);
+    g->st.n_pairs = n_pairs;
+    return finish_graph(ctx, sorted, n_pairs, n_vertices, g);
+}
+
+int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                    uint32_t n_vertices, kombgpu_graph *g) {
+    if (n_hits >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_hits >= 2^32 is not supported on one device");
+    const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
+    g->st.n_hits = n_hits;
+
+    // 1. (read, unitig) keys, sorted + unique  == per-read unitig SETS, mates merged
+    DevBuf<uint64_t> ha, hb;
+    DevBuf<uint32_t> info(ctx, 2);
+    KG_ALLOC(ctx, ha, n_hits);
+    KG_ALLOC(ctx, hb, n_hits);
+    if (!info) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    if (n_hits)
+        KG_LAUNCH(ctx, pack_hits_kernel, min(grid_for(n_hits, kThreads), 148u * 16u), kThreads, 0, read_key, unitig, n_hits,
+                  n_vertices, ha.p, info.p);
+    uint32_t h_info[2] = {0, 0};
+    KG_TRY(read_back(ctx, info.p, h_info, 2));
+    if (h_info[1]) return ctx_fail(ctx, KOMBGPU_EINVAL, "unitig id >= n_vertices (%u)", n_vertices);
+    uint64_t *sorted = ha.p;
+    RadixPass passes[8];
+    int np = plan_radix_passes(0, bn, 32, 32 + bits_for(h_info[0]), passes);
+    KG_TRY(radix_sort_u64(ctx, ha.p, hb.p, n_hits, passes, np, &sorted));
+    uint64_t *other = sorted == ha.p ? hb.p : ha.p;
+    DevBuf<uint32_t> d_cnt(ctx, 1);
+    if (!d_cnt) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_TRY((device_scan<uint32_t>(ctx, n_hits, HeadFlagU64{sorted}, CompactKeysU64{sorted, other}, d_cnt.p)));
+    uint32_t n_uniq = 0;
+    KG_TRY(read_back(ctx, d_cnt.p, &n_uniq, 1));
+    const uint64_t *hits = other;  // sorted unique hits, n_uniq of them
+    g->st.n_unique_hits = n_uniq;
+
+    // 2. reads with >= 2 unitigs -> segments; pairs per segment -> offsets
+    DevBuf<uint32_t> seg_head, seg_tail;
+    DevBuf<uint64_t> d_tot(ctx, 1);
+    KG_ALLOC(ctx, seg_head, (size_t)n_uniq / 2 + 1);
+    KG_ALLOC(ctx, seg_tail, (size_t)n_uniq / 2 + 1);
+    if (!d_tot) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_TRY((device_scan<uint64_t>(ctx, n_uniq, SegFlagIn{hits, n_uniq}, SegFlagOut{seg_head.p, seg_tail.p}, d_tot.p)));
+    uint64_t seg_tot = 0;
+    KG_TRY(read_back(ctx, d_tot.p, &seg_tot, 1));
+    const uint32_t n_seg = (uint32_t)(seg_tot >> 32);
+    DevBuf<uint64_t> seg_base;
+    KG_ALLOC(ctx, seg_base, (size_t)n_seg + 1);
+    KG_TRY((device_scan<uint64_t>(ctx, n_seg, SegPairsIn{seg_head.p, seg_tail.p}, SegPairsOut{seg_base.p}, d_tot.p)));
+    uint64_t n_pairs = 0;
+    KG_TRY(read_back(ctx, d_tot.p, &n_pairs, 1));
+    g->st.n_pairs = n_pairs;
+    if (n_pairs >= (1ull << 32))
+        return ctx_fail(ctx, KOMBGPU_EINVAL, "%llu clique pairs exceed the 2^32 per-device limit", (unsigned long long)n_pairs);
+
+    // 3. emit all pairs, sort, unique -> edges -> CSR
+    DevBuf<uint64_t> pa, pb;
+    KG_ALLOC(ctx, pa, n_pairs);
+    KG_ALLOC(ctx, pb, n_pairs);
+    uint64_t *psorted = pa.p;
+    if (n_pairs) {
+        const uint32_t n_tiles = ceil_div_u64(n_pairs, kEmitTile);
+        DevBuf<uint32_t> tile_seg;
+        KG_ALLOC(ctx, tile_seg, n_tiles);
+        KG_LAUNCH(ctx, emit_partition_kernel, grid_for(n_tiles, kThreads), kThreads, 0, seg_base.p, n_seg, n_tiles, tile_seg.p);
+        KG_LAUNCH(ctx, emit_pairs_kernel, n_tiles, kThreads, 0, hits, seg_head.p, seg_base.p, n_seg, tile_seg.p, n_tiles,
+                  n_pairs, pa.p);
+        // the hit buffers are no longer needed once the pairs exist
+        int npp = plan_radix_passes(0, bn, 32, 32 + bn, passes);
+        KG_TRY(radix_sort_u64(ctx, pa.p, pb.p, n_pairs, passes, npp, &psorted));
+    }
+    ha.release();
+    hb.release();
+    return finish_graph(ctx, psorted, n_pairs, n_vertices, g);
+}
+
+void graph_release(kombgpu_graph *g) {
+    if (!g || !g->ctx) return;
+    kombgpu_ctx *ctx = g->ctx;
+    if (g->edges) ws_free(ctx, g->edges);
+    if (g->row_ptr) ws_free(ctx, g->row_ptr);
+    if (g->col) ws_free(ctx, g->col);
+    if (g->deg) ws_free(ctx, g->deg);
+    if (g->core) ws_free(ctx, g->core);
+    if (g->score) ws_free(ctx, g->score);
+    g->edges = nullptr; g->row_ptr = nullptr; g->col = nullptr; g->deg = nullptr; g->core = nullptr; g->score = nullptr;
+}
+
+}  // namespace kg

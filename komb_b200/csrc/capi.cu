@@ -1,0 +1,386 @@
+// capi.cu — the extern "C" boundary of libkombgpu.so (include/kombgpu.h):
+// context + workspace arena, host<->device staging, stage sequencing and timing.
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "graph.cuh"
+
+namespace kg {
+
+static thread_local std::string g_create_error;
+
+int ctx_fail(kombgpu_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    if (code == KOMBGPU_ECUDA) cudaGetLastError();  // clear the sticky-free error state
+    return code;
+}
+
+// ---- workspace arena ---------------------------------------------------------
+// Device memory is cached per context: a steady-state run of the path performs
+// no cudaMalloc/cudaFree at all.
+void *ws_alloc(kombgpu_ctx *ctx, size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (bytes == 0) bytes = 512;
+    int best = -1;
+    for (size_t i = 0; i < ctx->arena.size(); ++i) {
+        const ArenaBlock &b = ctx->arena[i];
+        if (b.in_use || b.bytes < bytes) continue;
+        if (b.bytes > 2 * bytes + (1u << 20)) continue;  // do not burn a huge block on a tiny request
+        if (best < 0 || b.bytes < ctx->arena[best].bytes) best = (int)i;
+    }
+    if (best >= 0) {
+        ctx->arena[best].in_use = true;
+        return ctx->arena[best].ptr;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        // give cached-but-idle blocks back and retry once
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i < ctx->arena.size();) {
+            if (!ctx->arena[i].in_use) {
+                cudaFree(ctx->arena[i].ptr);
+                ctx->arena.erase(ctx->arena.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    ctx->arena.push_back(ArenaBlock{p, bytes, true});
+    return p;
+}
+
+void ws_free(kombgpu_ctx *ctx, void *p) {
+    if (!p) return;
+    for (auto &b : ctx->arena)
+        if (b.ptr == p) { b.in_use = false; return; }
+}
+
+void ws_trim(kombgpu_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < ctx->arena.size();) {
+        if (!ctx->arena[i].in_use) {
+            cudaFree(ctx->arena[i].ptr);
+            ctx->arena.erase(ctx->arena.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+}
+
+namespace {
+
+struct StageTimer {
+    kombgpu_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit StageTimer(kombgpu_ctx *c) : ctx(c) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    float stop() {
+        float ms = 0.f;
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+    ~StageTimer() {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
+template <typename T>
+int upload(kombgpu_ctx *ctx, DevBuf<T> &dst, const T *host, size_t count) {
+    KG_ALLOC(ctx, dst, count);
+    if (count) KG_CUDA(ctx, cudaMemcpyAsync(dst.p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return KOMBGPU_OK;
+}
+
+template <typename T>
+int download(kombgpu_ctx *ctx, const T *dev, T *host, size_t count) {
+    if (count == 0) return KOMBGPU_OK;
+    KG_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KOMBGPU_OK;
+}
+
+__global__ void unpack_edges_kernel(const uint64_t *__restrict__ edges, uint64_t n_edges, uint32_t *__restrict__ u,
+                                    uint32_t *__restrict__ v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = edges[i];
+        u[i] = (uint32_t)(e >> 32);
+        v[i] = (uint32_t)e;
+    }
+}
+
+typedef int (*BuildFn)(kombgpu_ctx *, const uint32_t *, const uint32_t *, uint64_t, uint32_t, kombgpu_graph *);
+
+int build_common(kombgpu_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t count, uint32_t n, bool host_inputs,
+                 BuildFn fn, kombgpu_graph **out) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if (!out || (count && (!a || !b))) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    *out = nullptr;
+    if (n >= 0xfffffffeu) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_vertices too large");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    kombgpu_graph *g = new (std::nothrow) kombgpu_graph();
+    if (!g) return ctx_fail(ctx, KOMBGPU_ENOMEM, "host allocation");
+    g->ctx = ctx;
+    g->st.max_coreness = -1;
+    const uint64_t launches0 = ctx->launches;
+    int rc;
+    {
+        DevBuf<uint32_t> da, db;
+        const uint32_t *pa = a, *pb = b;
+        StageTimer timer(ctx);  // host-input copies are part of the build time when inputs are on the host
+        rc = KOMBGPU_OK;
+        if (host_inputs) {
+            rc = upload(ctx, da, a, count);
+            if (rc == KOMBGPU_OK) rc = upload(ctx, db, b, count);
+            pa = da.p;
+            pb = db.p;
+        }
+        if (rc == KOMBGPU_OK) rc = fn(ctx, pa, pb, count, n, g);
+        g->st.ms_build = timer.stop();
+    }
+    g->st.kernel_launches = ctx->launches - launches0;
+    if (rc != KOMBGPU_OK) {
+        graph_release(g);
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return KOMBGPU_OK;
+}
+
+}  // namespace
+}  // namespace kg
+
+using namespace kg;
+
+extern "C" {
+
+int kombgpu_abi_version(void) { return KOMBGPU_ABI_VERSION; }
+
+int kombgpu_ctx_create(int device, kombgpu_ctx **out) {
+    if (!out) return KOMBGPU_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return ctx_fail(nullptr, KOMBGPU_ENODEV, "no CUDA device available (%s); libkombgpu has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return ctx_fail(nullptr, KOMBGPU_EINVAL, "device %d out of range [0, %d)", device, count);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return ctx_fail(nullptr, KOMBGPU_ENODEV, "device %d is sm_%d%d; libkombgpu is built for sm_100a (B200) only", device,
+                        prop.major, prop.minor);
+    if (!prop.cooperativeLaunch) return ctx_fail(nullptr, KOMBGPU_ENODEV, "device lacks cooperative launch");
+    if (cudaSetDevice(device) != cudaSuccess) return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaSetDevice(%d) failed", device);
+    kombgpu_ctx *ctx = new (std::nothrow) kombgpu_ctx();
+    if (!ctx) return ctx_fail(nullptr, KOMBGPU_ENOMEM, "host allocation");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaStreamCreate failed");
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->pinned_bytes = 4096;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        cudaGetLastError();
+    }
+    *out = ctx;
+    return KOMBGPU_OK;
+}
+
+void kombgpu_ctx_destroy(kombgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->arena) cudaFree(b.ptr);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int kombgpu_ctx_set_stream(kombgpu_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return KOMBGPU_OK;
+}
+
+const char *kombgpu_last_error(const kombgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int kombgpu_ctx_trim(kombgpu_ctx *ctx) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    ws_trim(ctx);
+    return KOMBGPU_OK;
+}
+
+int kombgpu_build_graph(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                        uint32_t n_vertices, kombgpu_graph **out) {
+    return build_common(ctx, read_key, unitig, n_hits, n_vertices, true, build_from_hits, out);
+}
+int kombgpu_build_graph_dev(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                            uint32_t n_vertices, kombgpu_graph **out) {
+    return build_common(ctx, read_key, unitig, n_hits, n_vertices, false, build_from_hits, out);
+}
+int kombgpu_graph_from_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                             kombgpu_graph **out) {
+    return build_common(ctx, u, v, n_pairs, n_vertices, true, build_from_pairs, out);
+}
+int kombgpu_graph_from_edges_dev(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs,
+                                 uint32_t n_vertices, kombgpu_graph **out) {
+    return build_common(ctx, u, v, n_pairs, n_vertices, false, build_from_pairs, out);
+}
+
+void kombgpu_graph_destroy(kombgpu_graph *g) {
+    if (!g) return;
+    graph_release(g);
+    delete g;
+}
+
+int kombgpu_graph_counts(const kombgpu_graph *g, uint32_t *n_vertices, uint64_t *n_edges) {
+    if (!g) return KOMBGPU_EINVAL;
+    if (n_vertices) *n_vertices = g->n;
+    if (n_edges) *n_edges = g->n_edges;
+    return KOMBGPU_OK;
+}
+
+int kombgpu_graph_edges(const kombgpu_graph *g, uint32_t *u, uint32_t *v) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (!u || !v) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    if (g->n_edges == 0) return KOMBGPU_OK;
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> du, dv;
+    KG_ALLOC(ctx, du, g->n_edges);
+    KG_ALLOC(ctx, dv, g->n_edges);
+    KG_LAUNCH(ctx, unpack_edges_kernel, min(ceil_div_u64(g->n_edges, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->edges,
+              g->n_edges, du.p, dv.p);
+    KG_TRY(download(ctx, du.p, u, g->n_edges));
+    return download(ctx, dv.p, v, g->n_edges);
+}
+
+int kombgpu_graph_csr(const kombgpu_graph *g, uint64_t *row_ptr, uint32_t *col) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (!row_ptr || !col) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    KG_TRY(download(ctx, g->row_ptr, row_ptr, (size_t)g->n + 1));
+    return download(ctx, g->col, col, 2 * g->n_edges);
+}
+
+int kombgpu_degree(const kombgpu_graph *g, int32_t *degree) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (!degree) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return download(ctx, g->deg, degree, g->n);
+}
+
+int kombgpu_coreness(kombgpu_graph *g, int32_t *coreness) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!g->has_core) {
+        const uint64_t launches0 = ctx->launches;
+        StageTimer timer(ctx);
+        int rc = peel_coreness(g);
+        g->st.ms_peel = timer.stop();
+        g->st.kernel_launches += ctx->launches - launches0;
+        if (rc != KOMBGPU_OK) return rc;
+    }
+    if (coreness) return download(ctx, g->core, coreness, g->n);
+    return KOMBGPU_OK;
+}
+
+int kombgpu_corea(kombgpu_ctx *ctx, const int32_t *coreness, const int32_t *degree, uint32_t n, int key_mode, double *score) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if (n && (!coreness || !degree || !score)) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    for (uint32_t i = 0; i < n; ++i)
+        if (coreness[i] < 0 || degree[i] < 0) return ctx_fail(ctx, KOMBGPU_EINVAL, "negative coreness/degree at %u", i);
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<int32_t> dc, dd;
+    DevBuf<double> ds;
+    KG_TRY(upload(ctx, dc, coreness, n));
+    KG_TRY(upload(ctx, dd, degree, n));
+    KG_ALLOC(ctx, ds, n);
+    double mx = 0.0;
+    KG_TRY(corea_scores(ctx, dc.p, dd.p, n, key_mode, ds.p, &mx));
+    return download(ctx, ds.p, score, n);
+}
+
+int kombgpu_graph_corea(kombgpu_graph *g, int key_mode, double *score) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (!g->has_core) return ctx_fail(ctx, KOMBGPU_ESTATE, "kombgpu_graph_corea needs kombgpu_coreness first");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!g->score) {
+        g->score = static_cast<double *>(ws_alloc(ctx, (g->n ? g->n : 1) * sizeof(double)));
+        if (!g->score) return ctx_fail(ctx, KOMBGPU_ENOMEM, "score array");
+    }
+    {
+        const uint64_t launches0 = ctx->launches;
+        StageTimer timer(ctx);
+        int rc = corea_scores(ctx, g->core, g->deg, g->n, key_mode, g->score, &g->max_score);
+        g->st.ms_corea = timer.stop();
+        g->st.kernel_launches += ctx->launches - launches0;
+        if (rc != KOMBGPU_OK) return rc;
+        g->has_score = true;
+    }
+    if (score) return download(ctx, g->score, score, g->n);
+    return KOMBGPU_OK;
+}
+
+int kombgpu_graph_summary(const kombgpu_graph *g, int32_t *max_coreness, double *max_score) {
+    if (!g) return KOMBGPU_EINVAL;
+    if (!g->has_core) return ctx_fail(g->ctx, KOMBGPU_ESTATE, "coreness not computed yet");
+    if (max_coreness) *max_coreness = g->st.max_coreness;
+    if (max_score) *max_score = g->has_score ? g->max_score : 0.0;
+    return KOMBGPU_OK;
+}
+
+int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode) {
+    KG_TRY(kombgpu_coreness(g, nullptr));
+    return kombgpu_graph_corea(g, key_mode, nullptr);
+}
+
+int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out) {
+    if (!g || !out) return KOMBGPU_EINVAL;
+    *out = g->st;
+    return KOMBGPU_OK;
+}
+
+int kombgpu_graph_device_arrays(const kombgpu_graph *g, const uint64_t **row_ptr, const uint32_t **col,
+                                const uint64_t **edges_packed, const int32_t **degree, const int32_t **coreness,
+                                const double **score) {
+    if (!g) return KOMBGPU_EINVAL;
+    if (row_ptr) *row_ptr = g->row_ptr;
+    if (col) *col = g->col;
+    if (edges_packed) *edges_packed = g->edges;
+    if (degree) *degree = g->deg;
+    if (coreness) *coreness = g->has_core ? g->core : nullptr;
+    if (score) *score = g->has_score ? g->score : nullptr;
+    return KOMBGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// corea.cu — stage 3: CORE-A anomaly score.
+//
+// Restates CoreA::getAnomalyScore / fractionalRank (src/CoreA.h:109-187):
+//   key_i   = coreness_i * n + degree_i            (int32 wrap = "ref32", quirk Q5)
+//   a_i     = descending average-tie rank of degree_i
+//   b_i     = descending average-tie rank of key_i
+//   score_i = | ln a_i - ln b_i |
+// The reference ranks in O(n * distinct values); here
+//   degree ranks: histogram over [0, max degree] -> prefix scan -> rank LUT
+//   key ranks   : radix sort of (key << 32 | vertex) -> run boundaries -> rank
+// Ranks are exact half-integers in FP64 (class [s, e) of the ascending order has
+// descending average rank n - (s + e - 1) / 2); only ln() can differ from glibc,
+// by <= 1 ulp, far inside the 1e-6 relative tolerance the path is held to.
+#include "graph.cuh"
+#include "primitives.cuh"
+
+namespace kg {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSmemBins = 4096;
+
+inline uint32_t grid_for(uint64_t n, int per_block, uint32_t cap) {
+    uint32_t g = ceil_div_u64(n ? n : 1, per_block);
+    return g < cap ? g : cap;
+}
+
+// mm[0] = max degree, mm[1] = max coreness
+__global__ void __launch_bounds__(kThreads) max2_kernel(const int32_t *__restrict__ deg, const int32_t *__restrict__ core,
+                                                        uint32_t n, int32_t *__restrict__ mm) {
+    int32_t md = 0, mc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        md = max(md, deg[i]);
+        mc = max(mc, core[i]);
+    }
+    md = warp_reduce_max(md);
+    mc = warp_reduce_max(mc);
+    if (lane_id() == 0) {
+        if (md) atomicMax(&mm[0], md);
+        if (mc) atomicMax(&mm[1], mc);
+    }
+}
+
+// degree histogram: low degrees (the bulk of a power-law graph) are counted in a
+// per-CTA shared-memory histogram, the tail goes straight to global atomics.
+__global__ void __launch_bounds__(kThreads) degree_hist_kernel(const int32_t *__restrict__ deg, uint32_t n,
+                                                               uint32_t n_bins, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_hist[kSmemBins];
+    for (int b = threadIdx.x; b < kSmemBins; b += kThreads) s_hist[b] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t d = (uint32_t)deg[i];
+        if (d < kSmemBins) atomicAdd(&s_hist[d], 1u);
+        else atomicAdd(&hist[d], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < kSmemBins && b < n_bins; b += kThreads) {
+        uint32_t c = s_hist[b];
+        if (c) atomicAdd(&hist[b], c);
+    }
+}
+
+// rank_lut[d] = #{degree > d} + (count(d) + 1) / 2
+struct HistIn {
+    const uint32_t *hist;
+    __device__ uint32_t operator()(uint64_t d) const { return hist[d]; }
+};
+struct RankLutOut {
+    double *lut;
+    uint32_t n;
+    __device__ void operator()(uint64_t d, uint32_t less, uint32_t cnt) const {
+        uint32_t greater = n - less - cnt;
+        lut[d] = (double)greater + 0.5 * (double)(cnt + 1u);
+    }
+};
+
+// sort key: high word orders the vertices by CORE-A key, low word = vertex id
+__global__ void __launch_bounds__(kThreads) pack_rank_keys_kernel(const int32_t *__restrict__ core,
+                                                                  const int32_t *__restrict__ deg, uint32_t n, int mode,
+                                                                  int deg_bits, uint64_t *__restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t hi;
+        if (mode == 0) {
+            // (int32)(coreness * n + degree) with two's complement wrap; flip the sign bit for unsigned order
+            hi = ((uint32_t)core[i] * n + (uint32_t)deg[i]) ^ 0x80000000u;
+        } else if (mode == 1) {
+            // exact: order of coreness * n + degree == lexicographic (coreness, degree) since degree < n
+            hi = ((uint32_t)core[i] << deg_bits) | (uint32_t)deg[i];
+        } else if (mode == 2) {
+            hi = (uint32_t)deg[i];   // wide fallback, first sort: by degree
+        } else {
+            hi = 0;
+        }
+        keys[i] = ((uint64_t)hi << 32) | (uint32_t)i;
+    }
+}
+
+// wide fallback, second sort: re-key the degree-sorted sequence by coreness
+__global__ void __launch_bounds__(kThreads) rekey_by_core_kernel(const int32_t *__restrict__ core, uint32_t n,
+                                                                 uint64_t *__restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = (uint32_t)keys[i];
+        keys[i] = ((uint64_t)(uint32_t)core[v] << 32) | v;
+    }
+}
+
+// class heads of the sorted sequence.  wide = compare (coreness, degree) through
+// the vertex id instead of the packed high word.
+struct ClassFlagIn {
+    const uint64_t *keys;
+    const int32_t *core;
+    const int32_t *deg;
+    int wide;
+    __device__ uint32_t operator()(uint64_t i) const {
+        if (i == 0) return 1u;
+        if (!wide) return (keys[i] >> 32) != (keys[i - 1] >> 32) ? 1u : 0u;
+        uint32_t a = (uint32_t)keys[i], b = (uint32_t)keys[i - 1];
+        return (core[a] != core[b] || deg[a] != deg[b]) ? 1u : 0u;
+    }
+};
+struct ClassFlagOut {
+    uint32_t *head_pos;  // [n_classes] start position of each class
+    uint32_t *cls;       // [n] class of each sorted position
+    __device__ void operator()(uint64_t i, uint32_t prefix, uint32_t flag) const {
+        if (flag) head_pos[prefix] = (uint32_t)i;
+        cls[i] = prefix + flag - 1u;
+    }
+};
+
+__global__ void __launch_bounds__(kThreads) score_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ cls,
+                                                         const uint32_t *__restrict__ head_pos,
+                                                         const uint32_t *__restrict__ n_classes_dev,
+                                                         const int32_t *__restrict__ deg, const double *__restrict__ deg_lut,
+                                                         uint32_t n, double *__restrict__ score,
+                                                         unsigned long long *__restrict__ max_bits) {
+    const uint32_t n_classes = *n_classes_dev;
+    double local_max = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = cls[i];
+        const uint32_t s = head_pos[c];
+        const uint32_t e = c + 1 < n_classes ? head_pos[c + 1] : n;
+        // ascending positions [s, e)  ->  descending ranks n-e+1 .. n-s, mean n - (s+e-1)/2
+        const double key_rank = (double)n - 0.5 * (double)((uint64_t)s + e - 1);
+        const uint32_t v = (uint32_t)keys[i];
+        const double deg_rank = deg_lut[deg[v]];
+        const double sc = fabs(log(deg_rank) - log(key_rank));
+        score[v] = sc;
+        local_max = fmax(local_max, sc);
+    }
+    // scores are >= 0, so their bit patterns order like unsigned integers
+    unsigned long long bits = (unsigned long long)__double_as_longlong(local_max);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(kFullMask, bits, o);
+        bits = t > bits ? t : bits;
+    }
+    if (lane_id() == 0 && bits) atomicMax(max_bits, bits);
+}
+
+}  // namespace
+
+int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint32_t n, int key_mode, double *score,
+                 double *max_score_host) {
+    *max_score_host = 0.0;
+    if (n == 0) return KOMBGPU_OK;
+    if (key_mode != KOMBGPU_KEY_REF32 && key_mode != KOMBGPU_KEY_EXACT64)
+        return ctx_fail(ctx, KOMBGPU_EINVAL, "unknown CORE-A key mode %d", key_mode);
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8u;
+
+    DevBuf<int32_t> mm(ctx, 2);
+    if (!mm) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    KG_LAUNCH(ctx, max2_kernel, grid_for(n, kThreads, cap), kThreads, 0, deg, core, n, mm.p);
+    int32_t h_mm[2] = {0, 0};
+    KG_TRY(read_back(ctx, mm.p, h_mm, 2));
+    const uint32_t max_deg = (uint32_t)h_mm[0], max_core = (uint32_t)h_mm[1];
+
+    // degree ranks through a histogram LUT
+    const uint32_t n_bins = max_deg + 1;
+    DevBuf<uint32_t> hist;
+    DevBuf<double> lut;
+    KG_ALLOC(ctx, hist, n_bins);
+    KG_ALLOC(ctx, lut, n_bins);
+    KG_CUDA(ctx, cudaMemsetAsync(hist.p, 0, (size_t)n_bins * sizeof(uint32_t), ctx->stream));
+    KG_LAUNCH(ctx, degree_hist_kernel, grid_for(n, kThreads * 8, cap), kThreads, 0, deg, n, n_bins, hist.p);
+    KG_TRY((device_scan<uint32_t>(ctx, n_bins, HistIn{hist.p}, RankLutOut{lut.p, n}, (uint32_t *)nullptr)));
+
+    // key ranks through a sort
+    DevBuf<uint64_t> ka, kb;
+    KG_ALLOC(ctx, ka, n);
+    KG_ALLOC(ctx, kb, n);
+    uint64_t *sorted = ka.p;
+    RadixPass passes[8];
+    int wide = 0;
+    if (key_mode == KOMBGPU_KEY_REF32) {
+        KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, 0, 0, ka.p);
+        int np = plan_radix_passes(32, 64, 0, 0, passes);
+        KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n, passes, np, &sorted));
+    } else {
+        const int db = bits_for(max_deg), cb = bits_for(max_core);
+        if (db + cb <= 32) {
+            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, 1, db, ka.p);
+            int np = plan_radix_passes(32, 32 + db + cb, 0, 0, passes);
+            KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n, passes, np, &sorted));
+        } else {
+            // (coreness, degree) does not fit 32 bits: LSD over the two fields with a re-key in between
+            wide = 1;
+            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, 2, 0, ka.p);
+            int np = plan_radix_passes(32, 32 + db, 0, 0, passes);
+            KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n, passes, np, &sorted));
+            uint64_t *other = sorted == ka.p ? kb.p : ka.p;
+            KG_LAUNCH(ctx, rekey_by_core_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, n, sorted);
+            np = plan_radix_passes(32, 32 + cb, 0, 0, passes);
+            uint64_t *sorted2 = sorted;
+            KG_TRY(radix_sort_u64(ctx, sorted, other, n, passes, np, &sorted2));
+            sorted = sorted2;
+        }
+    }
+
+    DevBuf<uint32_t> head_pos, cls, n_classes(ctx, 1);
+    DevBuf<unsigned long long> max_bits(ctx, 1);
+    KG_ALLOC(ctx, head_pos, n);
+    KG_ALLOC(ctx, cls, n);
+    if (!n_classes || !max_bits) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(max_bits.p, 0, sizeof(unsigned long long), ctx->stream));
+    KG_TRY((device_scan<uint32_t>(ctx, n, ClassFlagIn{sorted, core, deg, wide}, ClassFlagOut{head_pos.p, cls.p}, n_classes.p)));
+    KG_LAUNCH(ctx, score_kernel, grid_for(n, kThreads, cap), kThreads, 0, sorted, cls.p, head_pos.p, n_classes.p, deg, lut.p, n,
+              score, max_bits.p);
+    unsigned long long h_bits = 0;
+    KG_TRY(read_back(ctx, max_bits.p, &h_bits, 1));
+    memcpy(max_score_host, &h_bits, sizeof(double));
+    return KOMBGPU_OK;
+}
+
+}  // namespace kg

@@ -1,0 +1,39 @@
+// graph.cuh — the device-resident unitig graph and the stage entry points that
+// the C ABI (capi.cu) strings together.
+#pragma once
+
+#include "common.cuh"
+
+struct kombgpu_graph {
+    kombgpu_ctx *ctx = nullptr;
+    uint32_t n = 0;            // vertices (hit unitigs)
+    uint64_t n_edges = 0;      // simple undirected edges
+    uint64_t *edges = nullptr;   // [E]   packed (u << 32 | v), u < v, ascending
+    uint64_t *row_ptr = nullptr; // [n+1] CSR offsets of the symmetric graph
+    uint32_t *col = nullptr;     // [2E]  neighbours, every row ascending
+    int32_t *deg = nullptr;      // [n]
+    int32_t *core = nullptr;     // [n]   after peel
+    double *score = nullptr;     // [n]   after CORE-A
+    double max_score = 0.0;
+    bool has_core = false, has_score = false;
+    kombgpu_stats st{};
+};
+
+namespace kg {
+
+// stage 1 (build.cu) — inputs are device pointers
+int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                    uint32_t n_vertices, kombgpu_graph *g);
+int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                     kombgpu_graph *g);
+
+// stage 2 (peel.cu)
+int peel_coreness(kombgpu_graph *g);
+
+// stage 3 (corea.cu) — device pointers in, device score out; *max_score on host
+int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint32_t n, int key_mode, double *score,
+                 double *max_score_host);
+
+void graph_release(kombgpu_graph *g);
+
+}  // namespace kg

@@ -1,0 +1,120 @@
+// primitives.cuh — device-wide building blocks used by the graph build and
+// CORE-A stages: a generic three-phase prefix scan (also used as stream
+// compaction) and an LSD radix sort of 64-bit keys.  All HBM-bound integer work.
+#pragma once
+
+#include "common.cuh"
+
+namespace kg {
+
+// One radix pass sorts on bits [shift, shift+bits) (bits <= 8).
+struct RadixPass {
+    int shift;
+    int bits;
+};
+
+// Split the key bit ranges [lo0,hi0) and [lo1,hi1) (second may be empty) into
+// passes of at most 8 bits, least significant first.
+int plan_radix_passes(int lo0, int hi0, int lo1, int hi1, RadixPass *out /* >= 8 entries */);
+
+// Stable LSD radix sort.  `a` holds the keys, `b` is scratch of the same size;
+// returns in *sorted whichever of the two holds the result.
+int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const RadixPass *passes,
+                   int n_passes, uint64_t **sorted);
+
+#ifdef __CUDACC__
+
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// phase 1: per-tile sums of in(i)
+template <typename T, typename InFn>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(uint64_t n, InFn in, T *tile_sums) {
+    __shared__ T s_warp[kScanThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+    T acc = T(0);
+#pragma unroll 4
+    for (int j = 0; j < kScanItems; ++j) {
+        uint64_t i = base + (uint64_t)j * kScanThreads + threadIdx.x;
+        if (i < n) acc += in(i);
+    }
+    acc = warp_reduce_add(acc);
+    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = threadIdx.x < kScanThreads / 32 ? s_warp[threadIdx.x] : T(0);
+        v = warp_reduce_add(v);
+        if (threadIdx.x == 0) tile_sums[blockIdx.x] = v;
+    }
+}
+
+// phase 2: one CTA turns tile sums into exclusive tile prefixes (+ grand total)
+template <typename T>
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(T *tile_sums, uint32_t n_tiles, T *total) {
+    __shared__ T s_scan[33];
+    T carry = T(0);
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        T v = i < n_tiles ? tile_sums[i] : T(0);
+        T tot;
+        T ex = block_excl_scan_add<T, 1024>(v, s_scan, &tot);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// phase 3: out(i, exclusive_prefix_i, in(i))
+template <typename T, typename InFn, typename OutFn>
+__global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint64_t n, InFn in, const T *tile_prefix, OutFn out) {
+    __shared__ T s_scan[kScanThreads / 32 + 1];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+    T carry = tile_prefix[blockIdx.x];
+    for (int j = 0; j < kScanItems; ++j) {
+        uint64_t i = base + (uint64_t)j * kScanThreads + threadIdx.x;
+        if (base + (uint64_t)j * kScanThreads >= n) break;  // uniform across the CTA
+        T v = i < n ? in(i) : T(0);
+        T tot;
+        T ex = block_excl_scan_add<T, kScanThreads>(v, s_scan, &tot);
+        if (i < n) out(i, carry + ex, v);
+        carry += tot;
+    }
+}
+
+// Exclusive prefix sum over in(0..n-1); out(i, prefix, value) is called once per
+// element; *total_dev (device, optional) receives the grand total.
+template <typename T, typename InFn, typename OutFn>
+int device_scan(kombgpu_ctx *ctx, uint64_t n, InFn in, OutFn out, T *total_dev) {
+    if (n == 0) {
+        if (total_dev) KG_CUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(T), ctx->stream));
+        return KOMBGPU_OK;
+    }
+    uint32_t n_tiles = ceil_div_u64(n, kScanTile);
+    DevBuf<T> tiles;
+    KG_ALLOC(ctx, tiles, n_tiles);
+    KG_LAUNCH(ctx, (scan_reduce_kernel<T, InFn>), n_tiles, kScanThreads, 0, n, in, tiles.p);
+    KG_LAUNCH(ctx, (scan_tiles_kernel<T>), 1, 1024, 0, tiles.p, n_tiles, total_dev);
+    KG_LAUNCH(ctx, (scan_downsweep_kernel<T, InFn, OutFn>), n_tiles, kScanThreads, 0, n, in, tiles.p, out);
+    return KOMBGPU_OK;
+}
+
+// functors shared by several stages ------------------------------------------------
+
+// head-of-run predicate on a sorted key array: 1 when keys[i] != keys[i-1]
+struct HeadFlagU64 {
+    const uint64_t *keys;
+    __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+};
+// write keys[i] to dst[prefix] when flagged: adjacent-unique of a sorted array
+struct CompactKeysU64 {
+    const uint64_t *keys;
+    uint64_t *dst;
+    __device__ void operator()(uint64_t i, uint32_t pos, uint32_t flag) const {
+        if (flag) dst[pos] = keys[i];
+    }
+};
+
+#endif  // __CUDACC__
+
+}  // namespace kg

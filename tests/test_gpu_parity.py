@@ -1,0 +1,183 @@
+"""Parity of the CUDA path (through the C ABI, komb_b200.api -> libkombgpu.so)
+against the CPU oracle and the reference-generated golden fixtures.
+
+Bars (BASELINE.json north_star): edge list and per-unitig coreness bit-exact;
+CORE-A within 1e-6 relative (atol 1e-12) with an identical anomaly ranking.
+"""
+import numpy as np
+import pytest
+
+from conftest import (corea_case_names, komb2_case_names, load_corea_case,
+                      load_komb2_case)
+from komb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-6, 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import komb_b200
+    c = komb_b200.Context(0)
+    yield c
+    c.close()
+
+
+def check_graph_against_oracle(oracle, g, n, exp_edges):
+    gn, gm = g.counts()
+    assert (gn, gm) == (n, exp_edges.shape[0])
+    u, v = g.edges()
+    assert np.array_equal(oracle.pack_edges(u, v), exp_edges)            # edge list bit-exact, canonical order
+    exp_deg, exp_core = oracle.coreness(n, exp_edges)
+    assert np.array_equal(g.degree(), exp_deg)
+    row_ptr, col = g.csr()
+    assert np.array_equal(np.diff(row_ptr.astype(np.int64)), exp_deg)
+    # CSR rows: ascending, symmetric closure of the edge list
+    src = np.repeat(np.arange(n, dtype=np.uint64), exp_deg)
+    keys = (src << np.uint64(32)) | col.astype(np.uint64)
+    assert np.all(np.diff(keys.astype(np.int64)) > 0) if keys.size > 1 else True
+    eu, ev = oracle.unpack_edges(exp_edges)
+    sym = np.sort(np.concatenate([oracle.pack_edges(eu, ev), oracle.pack_edges(ev, eu)]))
+    assert np.array_equal(keys, sym)
+    core = g.coreness()
+    assert np.array_equal(core, exp_core)                                  # coreness bit-exact
+    return exp_deg, exp_core
+
+
+def check_corea(oracle, got, core, deg, mode):
+    exp = oracle.corea(core, deg, mode)
+    np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
+    # identical anomaly ranking: descending score, ties by vertex id; scores that are
+    # mathematically tied (same rank pair) are bit-identical within each implementation
+    assert np.array_equal(np.argsort(-got, kind="stable"), np.argsort(-exp, kind="stable"))
+
+
+@pytest.mark.parametrize("name", komb2_case_names())
+def test_golden_komb2_cases(ctx, oracle_mod, name):
+    sam1, sam2, exp = load_komb2_case(name)
+    rk, ut, names = oracle_mod.intern_hits([oracle_mod.tokenise_sam(sam1, exp["threads"]),
+                                            oracle_mod.tokenise_sam(sam2, exp["threads"])])
+    with ctx.build_graph(rk, ut, len(names)) as g:
+        u, v = g.edges()
+        got_edges = {tuple(sorted((names[a], names[b]))) for a, b in zip(u.tolist(), v.tolist())}
+        assert got_edges == exp["edges"]
+        core, deg = g.coreness(), g.degree()
+        assert {names[i]: (int(core[i]), int(deg[i])) for i in range(len(names))} == exp["kcore"]
+        score = g.corea()
+        for i, nm in enumerate(names):
+            assert abs(score[i] - float(exp["score_text"][nm])) <= 5.0e-7 + 1e-12
+        assert f"{score[i]:f}" is not None
+        mc, ms = g.summary()
+        assert f"Dense Ratio: {float(mc // 2):f}" in exp["stdout_info"]
+        assert f"Max CoreA score: {ms:f}" in exp["stdout_info"]
+
+
+@pytest.mark.parametrize("name", corea_case_names())
+def test_golden_corea_cases(ctx, name):
+    core, deg, ref = load_corea_case(name)
+    got = ctx.corea(core, deg)                       # ref32 keys, like the reference
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("seed,n,n_pairs", [(0, 1000, 15000), (1, 50000, 400000), (2, 300000, 3000000)])
+def test_hits_to_scores_vs_oracle(ctx, oracle_mod, seed, n, n_pairs):
+    m1, m2 = synth.metagenome_hits(n, n_pairs, seed=seed)
+    rk = np.concatenate([m1.read_key, m2.read_key])
+    ut = np.concatenate([m1.unitig, m2.unitig])
+    exp_edges, exp_p, exp_s = oracle_mod.build_edges(rk, ut)
+    with ctx.build_graph(rk, ut, n) as g:
+        deg, core = check_graph_against_oracle(oracle_mod, g, n, exp_edges)
+        st = g.stats()
+        assert (st["n_hits"], st["n_unique_hits"], st["n_pairs"], st["n_edges"]) == (rk.shape[0], exp_s, exp_p, exp_edges.shape[0])
+        assert st["max_degree"] == deg.max() and st["max_coreness"] == core.max()
+        for mode in (oracle_mod.KEY_REF32, oracle_mod.KEY_EXACT64):
+            check_corea(oracle_mod, g.corea(mode), core, deg, mode)
+
+
+def test_repeat_heavy_reads(ctx, oracle_mod):
+    """A few reads with hundreds of hits (bwa -a on repeats): quadratic pair blow-up."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    rk = [np.full(700, 0), np.full(350, 1), np.repeat(np.arange(2, 2002), 2)]
+    ut = [rng.integers(0, n, 700), rng.integers(0, 900, 350), rng.integers(0, n, 4000)]
+    rk, ut = np.concatenate(rk).astype(np.uint32), np.concatenate(ut).astype(np.uint32)
+    exp_edges, exp_p, _ = oracle_mod.build_edges(rk, ut)
+    with ctx.build_graph(rk, ut, n) as g:
+        check_graph_against_oracle(oracle_mod, g, n, exp_edges)
+        assert g.stats()["n_pairs"] == exp_p
+
+
+@pytest.mark.parametrize("seed,scale,n,m", [(0, 10, 900, 12000), (1, 16, 50000, 600000), (2, 20, 800000, 8000000)])
+def test_rmat_edges_vs_oracle(ctx, oracle_mod, seed, scale, n, m):
+    u, v = synth.rmat_edges(scale, m, n_vertices=n, seed=seed)
+    exp_edges = oracle_mod.simplify(u, v)
+    with ctx.graph_from_edges(u, v, n) as g:
+        deg, core = check_graph_against_oracle(oracle_mod, g, n, exp_edges)
+        check_corea(oracle_mod, g.corea(oracle_mod.KEY_EXACT64), core, deg, oracle_mod.KEY_EXACT64)
+        check_corea(oracle_mod, g.corea(oracle_mod.KEY_REF32), core, deg, oracle_mod.KEY_REF32)
+
+
+def test_deep_core_ramp(ctx, oracle_mod):
+    """cfg5 in miniature: hundreds of dependent peeling levels."""
+    levels, per = 400, 6
+    u, v = synth.ramp_edges(levels, per)
+    n = levels * per + 50                      # plus isolated vertices
+    exp_edges = oracle_mod.simplify(u, v)
+    with ctx.graph_from_edges(u, v, n) as g:
+        _, core = check_graph_against_oracle(oracle_mod, g, n, exp_edges)
+        st = g.stats()
+        assert core.max() == levels == st["max_coreness"]
+        assert st["peel_levels"] == len(set(core.tolist()))
+
+
+def test_kats_and_edge_cases(ctx, oracle_mod):
+    def run(n, pairs):
+        u = np.array([p[0] for p in pairs], np.uint32)
+        v = np.array([p[1] for p in pairs], np.uint32)
+        with ctx.graph_from_edges(u, v, n) as g:
+            return g.coreness().tolist(), g.degree().tolist(), g.counts()[1]
+    k6 = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+    assert run(6, k6)[0] == [5] * 6
+    assert run(5, [(i, i + 1) for i in range(4)])[0] == [1] * 5
+    assert run(6, [(0, i) for i in range(1, 6)])[0] == [1] * 6
+    assert run(5, [(i, (i + 1) % 5) for i in range(5)])[0] == [2] * 5
+    assert run(8, k6 + [(6, 7)])[0] == [5] * 6 + [1, 1]
+    assert run(3, [(0, 1), (1, 0), (0, 0), (0, 1)]) == ([1, 1, 0], [1, 1, 0], 1)   # dup, reversed, loop, isolated
+    assert run(4, []) == ([0] * 4, [0] * 4, 0)                                       # no edges
+    assert run(1, [(0, 0)]) == ([0], [0], 0)                                         # only a loop
+    with ctx.build_graph(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 0) as g:    # empty input
+        assert g.counts() == (0, 0)
+        assert g.coreness().shape == (0,) and g.corea().shape == (0,)
+    # hits: single-unitig reads make vertices but no edges (degree-0 rows, quirk Q4)
+    with ctx.build_graph(np.array([0, 1, 2, 2], np.uint32), np.array([0, 1, 2, 2], np.uint32), 3) as g:
+        assert g.counts() == (3, 0)
+        assert g.coreness().tolist() == [0, 0, 0]
+        assert np.array_equal(g.corea(), np.zeros(3))
+
+
+def test_errors_are_reported_not_swallowed(ctx):
+    import komb_b200
+    with pytest.raises(komb_b200.KombGpuError) as e:
+        ctx.graph_from_edges(np.array([0, 7], np.uint32), np.array([1, 2], np.uint32), 5)   # id >= n
+    assert e.value.code == -1
+    with pytest.raises(komb_b200.KombGpuError):
+        ctx.build_graph(np.array([0], np.uint32), np.array([9], np.uint32), 3)
+    with ctx.graph_from_edges(np.array([0], np.uint32), np.array([1], np.uint32), 2) as g:
+        with pytest.raises(komb_b200.KombGpuError) as e2:
+            g.corea()                                                                         # before coreness
+        assert e2.value.code == -5
+
+
+def test_device_resident_inputs(ctx, oracle_mod):
+    import torch
+    u, v = synth.rmat_edges(14, 200000, n_vertices=12000, seed=9)
+    exp_edges = oracle_mod.simplify(u, v)
+    tu = torch.from_numpy(u.view(np.int32)).cuda()
+    tv = torch.from_numpy(v.view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    with ctx.graph_from_edges(tu, tv, 12000) as g:
+        check_graph_against_oracle(oracle_mod, g, 12000, exp_edges)
+        g.analyse()
+        arr = g.device_arrays()
+        assert all(arr[k] for k in ("row_ptr", "col", "edges_packed", "degree", "coreness", "score"))
