@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the KOMB hot path (hits -> graph -> k-core -> CORE-A).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path over one synthetic batch
+(BASELINE.json configs[1]: 1 M unitigs, 5 M read pairs, ~20 M hits per GPU).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_UNITIGS = 1_000_000
+N_READ_PAIRS = 5_000_000
+SEED = 11
+CPU_SAMPLE_READ_PAIRS = 625_000          # 1/8 of the workload's reads for the CPU arm
+METRIC = "hot-path hits/s (graph build + k-core peel + CORE-A), with peel edges/s and build hits/s"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref/komb2_ref =
+# reference sources compiled unmodified against oracle/igraph_shim), else the
+# oracle port.  Runs on a bounded sample of the same workload.
+# ---------------------------------------------------------------------------
+
+def cpu_reference_run(n_unitigs: int, sample_read_pairs: int, seed: int, threads: int) -> dict:
+    from komb_b200 import synth
+    from oracle import oracle
+    m1, m2 = synth.metagenome_hits(n_unitigs, sample_read_pairs, seed=seed)
+    n_hits = m1.n_hits + m2.n_hits
+    sample = (f"{sample_read_pairs} of {N_READ_PAIRS} read pairs ({n_hits} hits) over the same "
+              f"{n_unitigs} unitigs, seed {seed}")
+    if oracle.REF_KOMB2.exists():
+        with tempfile.TemporaryDirectory() as d:
+            d = Path(d)
+            (d / "out").mkdir()
+            (d / "r1.sam").write_bytes(synth.render_sam(m1, n_unitigs, 1, with_header=False))
+            (d / "r2.sam").write_bytes(synth.render_sam(m2, n_unitigs, 2, with_header=False))
+            synth.write_fasta(str(d / "u.fasta"), 4)
+            t0 = time.perf_counter()
+            cp = subprocess.run([str(oracle.REF_KOMB2), "-t", str(threads), "-l", "100", "-o", str(d / "out"),
+                                 "-i", str(d / "r1.sam"), "-j", str(d / "r2.sam"), "-u", str(d / "u.fasta")],
+                                capture_output=True, text=True)
+            wall = time.perf_counter() - t0
+            if cp.returncode != 0:
+                raise RuntimeError(f"komb2_ref failed: {cp.stderr[-400:]}")
+        stages = {m.group(1).strip(): float(m.group(2))
+                  for m in re.finditer(r"Time elapsed (?:for|doing) ([^:]+): ([0-9.]+) s", cp.stdout)}
+        total = stages.get("KOMB", wall)          # komb2's own end-to-end timer (komb2.cpp:141-143)
+        edges = int(re.search(r"Number of edges: (\d+)", cp.stdout).group(1))
+        kcore_s = stages.get("K-core decomposition")
+        return {"value": n_hits / total, "unit": "hits/s", "cores": threads, "kind": "reference",
+                "sample": sample + f"; komb2_ref -t {threads} from SAM text, {total:.2f} s (igraph stages are the shim's)",
+                "seconds": total, "n_hits": n_hits, "n_edges": edges,
+                "peel_edges_per_s": (edges / kcore_s) if kcore_s else None,
+                "stage_seconds": stages}
+    # port: the C restatement (single thread)
+    rk = np.concatenate([m1.read_key, m2.read_key]); ut = np.concatenate([m1.unitig, m2.unitig])
+    t0 = time.perf_counter()
+    edges, _, _ = oracle.build_edges(rk, ut)
+    t1 = time.perf_counter()
+    deg, core = oracle.coreness(n_unitigs, edges)
+    t2 = time.perf_counter()
+    oracle.corea(core, deg, oracle.KEY_REF32)
+    t3 = time.perf_counter()
+    return {"value": n_hits / (t3 - t0), "unit": "hits/s", "cores": 1, "kind": "port",
+            "sample": sample + "; oracle/komb_oracle.c from integer hits (no SAM parsing)",
+            "seconds": t3 - t0, "n_hits": n_hits, "n_edges": int(edges.shape[0]),
+            "peel_edges_per_s": edges.shape[0] / (t2 - t1), "stage_seconds": {"build": t1 - t0, "peel": t2 - t1, "corea": t3 - t2}}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(N_UNITIGS, CPU_SAMPLE_READ_PAIRS // 4, SEED, threads)   # ~5 s per step
+        if i >= args.warmup:
+            vals.append(r)
+        last = r
+    v = float(np.mean([r["value"] for r in vals])) if vals else last["value"]
+    secs = float(np.mean([r["seconds"] for r in vals])) if vals else last["seconds"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "hits/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 ids, f64 scores", "data": "synthetic",
+        "config": {"workload": "cfg2 sample: metagenome hits, 1M unitigs, bounded read sample (CPU arm)",
+                   "n_unitigs": N_UNITIGS, "seed": SEED},
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": v, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "peel_edges_per_s": last.get("peel_edges_per_s"),
+    }
+    line["cpu_baseline"]["value"] = v
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import komb_b200
+    from komb_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        raise SystemExit("multi-GPU path not wired into bench.py yet")
+
+    hbm_gbs, peak_src = load_peaks()
+    ctx = komb_b200.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)      # time on the stream the kernels are launched on
+
+    # synthetic hits (host, pinned) and a device-resident copy
+    m1, m2 = synth.metagenome_hits(N_UNITIGS, N_READ_PAIRS, seed=SEED)
+    rk_h = torch.from_numpy(np.concatenate([m1.read_key, m2.read_key]).view(np.int32)).pin_memory()
+    ut_h = torch.from_numpy(np.concatenate([m1.unitig, m2.unitig]).view(np.int32)).pin_memory()
+    rk_d = rk_h.cuda(non_blocking=True)
+    ut_d = ut_h.cuda(non_blocking=True)
+    n_hits = rk_h.numel()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_device():
+        g = ctx.build_graph(rk_d, ut_d, N_UNITIGS)
+        g.analyse(komb_b200.KEY_REF32)
+        st = g.stats()
+        g.close()
+        return st
+
+    def step_e2e():
+        """The call a user of the C ABI makes: host hits in, every output the
+        komb2 host writes to its three files back on the host."""
+        g = ctx.build_graph(rk_h.numpy().view(np.uint32), ut_h.numpy().view(np.uint32), N_UNITIGS)
+        core = g.coreness()
+        score = g.corea(komb_b200.KEY_REF32)
+        deg = g.degree()
+        u, v = g.edges()
+        st = g.stats()
+        g.close()
+        return st, (u.nbytes + v.nbytes + core.nbytes + deg.nbytes + score.nbytes)
+
+    n_warm = 1 if args.profile else max(args.warmup, 3)
+    for _ in range(n_warm):
+        st = step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stats = []
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                 # L2 flush between timed iterations (outside the events)
+        torch.cuda.synchronize()
+        ev[i][0].record(stream)
+        stats.append(step_device())
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_per_step = float(np.mean(step_ms))
+    st = stats[-1]
+    H, P, E, n = st["n_hits"], st["n_pairs"], st["n_edges"], st["n_vertices"]
+
+    ms_build = float(np.mean([s["ms_build"] for s in stats]))
+    ms_peel = float(np.mean([s["ms_peel"] for s in stats]))
+    ms_corea = float(np.mean([s["ms_corea"] for s in stats]))
+    ms_peel_kernel = float(np.mean([s["ms_peel_kernel"] for s in stats]))
+
+    if args.profile:
+        print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "launches_per_step": st["kernel_launches"],
+                          "ms_build": ms_build, "ms_peel": ms_peel, "ms_corea": ms_corea}), flush=True)
+        ctx.close()
+        return
+
+    # e2e: host buffers, copies inside the timed region
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_t = []
+    d2h = 0
+    for _ in range(max(2, min(args.steps, 5))):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, d2h = step_e2e()
+        torch.cuda.synchronize()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t))
+
+    # algorithmic bytes (DESIGN.md "Roofline"): SURVEY 8(d)
+    b_peel = 24 * E + 16 * n
+    b_build = 8 * H + 16 * P + 8 * E + 8 * (n + 1)
+    b_corea = 32 * n
+    peel_gbs = b_peel / (ms_peel_kernel * 1e-3) / 1e9
+    line = {
+        "metric": METRIC,
+        "value": H / (ms_per_step * 1e-3),
+        "unit": "hits/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32/u64 ids, f64 scores", "data": "synthetic",
+        "config": {"workload": "cfg2: synthetic metagenome unitig graph, 1M unitigs, 5M read pairs (~20M hits), 1 GPU",
+                   "n_unitigs": n, "n_read_pairs": N_READ_PAIRS, "n_hits": H, "n_pairs": P, "n_edges": E,
+                   "max_coreness": st["max_coreness"], "peel_levels": st["peel_levels"], "seed": SEED,
+                   "corea_key": "ref32", "l2": "256 MB flush between timed steps; inputs (160 MB) exceed L2"},
+        "stages": {
+            "build": {"ms": ms_build, "hits_per_s": H / (ms_build * 1e-3), "algorithmic_bytes": b_build,
+                      "gbs": b_build / (ms_build * 1e-3) / 1e9, "frac_hbm": b_build / (ms_build * 1e-3) / 1e9 / hbm_gbs},
+            "peel": {"ms": ms_peel, "edges_per_s": E / (ms_peel * 1e-3), "algorithmic_bytes": b_peel,
+                     "gbs": b_peel / (ms_peel * 1e-3) / 1e9, "frac_hbm": b_peel / (ms_peel * 1e-3) / 1e9 / hbm_gbs},
+            "corea": {"ms": ms_corea, "vertices_per_s": n / (ms_corea * 1e-3), "algorithmic_bytes": b_corea,
+                      "gbs": b_corea / (ms_corea * 1e-3) / 1e9, "frac_hbm": b_corea / (ms_corea * 1e-3) / 1e9 / hbm_gbs},
+        },
+        "peel_edges_per_s": E / (ms_peel * 1e-3),
+        "build_hits_per_s": H / (ms_build * 1e-3),
+        "roofline": {"kernel": "peel_kernel (persistent cooperative frontier peel)", "bound": "hbm",
+                     "achieved": peel_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": peel_gbs / hbm_gbs,
+                     "traffic": None, "algorithmic_bytes": b_peel, "kernel_ms": ms_peel_kernel, "peak_source": peak_src},
+        "e2e": {"value": H / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": 8 * H, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            cb = cpu_reference_run(N_UNITIGS, CPU_SAMPLE_READ_PAIRS, SEED, os.cpu_count() or 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["peel_edges_per_s"] = cb.get("peel_edges_per_s")
+            line["cpu_baseline"]["stage_seconds"] = cb.get("stage_seconds")
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": "hits/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="minimal run for ncu: 1 warm-up + the timed steps only, no e2e / CPU legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

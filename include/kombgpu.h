@@ -65,6 +65,7 @@ typedef struct kombgpu_stats {
     float ms_build;          /* CUDA-event time: hits/edges -> CSR                     */
     float ms_peel;           /* CUDA-event time: k-core peel                           */
     float ms_corea;          /* CUDA-event time: CORE-A                                */
+    float ms_peel_kernel;    /* CUDA-event time of the persistent peel kernel alone    */
     uint64_t kernel_launches; /* kernels of this library launched for this graph       */
 } kombgpu_stats;
 

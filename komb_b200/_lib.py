@@ -23,7 +23,7 @@ class Stats(ctypes.Structure):
         ("n_hits", c_uint64), ("n_unique_hits", c_uint64), ("n_pairs", c_uint64), ("n_edges", c_uint64),
         ("n_vertices", c_uint32), ("max_degree", c_int32), ("max_coreness", c_int32),
         ("peel_levels", c_uint32), ("peel_rounds", c_uint32),
-        ("ms_build", c_float), ("ms_peel", c_float), ("ms_corea", c_float),
+        ("ms_build", c_float), ("ms_peel", c_float), ("ms_corea", c_float), ("ms_peel_kernel", c_float),
         ("kernel_launches", c_uint64),
     ]
 

@@ -303,8 +303,18 @@ int peel_coreness(kombgpu_graph *g) {
     uint32_t *q = queue.p, *aa = alive_a.p, *ab = alive_b.p;
     PeelState *sp = state.p;
     void *args[] = {&n_arg, &row_ptr, &col, &core, &q, &aa, &ab, &sp};
-    KG_CUDA(ctx, cudaLaunchCooperativeKernel((void *)peel_kernel, dim3(grid), dim3(kPeelThreads), args, 0, ctx->stream));
+    cudaEvent_t ev0, ev1;
+    KG_CUDA(ctx, cudaEventCreate(&ev0));
+    KG_CUDA(ctx, cudaEventCreate(&ev1));
+    KG_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    cudaError_t le = cudaLaunchCooperativeKernel((void *)peel_kernel, dim3(grid), dim3(kPeelThreads), args, 0, ctx->stream);
+    cudaEventRecord(ev1, ctx->stream);
     ctx->launches++;
+    if (le == cudaSuccess) le = cudaEventSynchronize(ev1);
+    if (le == cudaSuccess) cudaEventElapsedTime(&g->st.ms_peel_kernel, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (le != cudaSuccess) return ctx_fail(ctx, KOMBGPU_ECUDA, "peel kernel: %s", cudaGetErrorString(le));
 
     PeelState fin{};
     KG_TRY(read_back(ctx, state.p, &fin, 1));
