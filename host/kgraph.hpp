@@ -1,0 +1,232 @@
+// kgraph.hpp — komb::Kgraph for the B200 path: the reference's class and method
+// names (reference src/graph.h:41-63) kept as the host-side interface, every
+// compute step forwarded to libkombgpu through the C ABI (include/kombgpu.h).
+//
+//   reference method (src/graph.cpp)          here
+//   readSAM            :166-257               tokenise on the host -> integer hits + name table
+//   getEdgeInfo        :259-285               nothing left to do: the mate union happens on the
+//                                             device when both files' hits are sorted together
+//   generateGraph      :287-393               kombgpu_build_graph (pairs, dedup, CSR)
+//   readEdgeList       :395-453               writes edgelist.txt (simple edges, quirk Q7), prints
+//                                             GraphInfo, calls runCore
+//   runCore            :455-484               kombgpu_degree / kombgpu_coreness -> kcore.tsv
+//   anomalyDetection   :637-648               kombgpu_graph_corea -> CoreA_anomaly.txt
+//                       (CombineCoreA::run, src/CombineCoreA.h:16-43)
+// Errors follow the reference: a message on stderr and exit(EXIT_FAILURE)
+// (src/graph.cpp:58-61).
+#pragma once
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "kombgpu.h"
+#include "sam_tokenizer.hpp"
+
+namespace komb {
+
+struct HitTable {
+    SamTokens tokens;                 // spans into the mapped SAM files
+    std::vector<uint32_t> read_key;   // per hit
+    std::vector<uint32_t> unitig;     // per hit (vid)
+    std::vector<std::string> names;   // vid -> unitig name
+};
+
+inline double seconds_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() / 1000000.0;
+}
+
+// ---- fast text formatting ------------------------------------------------------
+inline char *put_u64(char *p, uint64_t v) {
+    char tmp[24];
+    int k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (k) *p++ = tmp[--k];
+    return p;
+}
+
+// format rows [lo, hi) with `fmt_row` into per-thread buffers, then write them in order
+template <typename RowFn>
+inline void write_rows(FILE *f, size_t n_rows, size_t max_row_bytes, int threads, RowFn fmt_row) {
+    threads = std::max(1, threads);
+    const size_t block = 1 << 16;
+    std::vector<std::vector<char>> buf(threads);
+    for (size_t base = 0; base < n_rows; base += block * threads) {
+        std::vector<size_t> used(threads, 0);
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+        for (int t = 0; t < threads; ++t) {
+            size_t lo = base + block * t, hi = std::min(n_rows, lo + block);
+            if (lo >= hi) continue;
+            buf[t].resize((hi - lo) * max_row_bytes);
+            char *p = buf[t].data();
+            for (size_t i = lo; i < hi; ++i) p = fmt_row(p, i);
+            used[t] = (size_t)(p - buf[t].data());
+        }
+        for (int t = 0; t < threads; ++t)
+            if (used[t]) fwrite(buf[t].data(), 1, used[t], f);
+    }
+}
+
+class Kgraph {
+    uint32_t _threads;
+    uint64_t _readlength;
+    kombgpu_ctx *_ctx = nullptr;
+    kombgpu_graph *_graph = nullptr;
+    int _key_mode = KOMBGPU_KEY_REF32;
+
+    [[noreturn]] void fileNotFoundError(const std::string &path) {
+        std::cerr << "File " << path << " could not be opened. Exiting..." << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    [[noreturn]] void gpuError(const char *what, int rc) {
+        std::cerr << "komb2: " << what << " failed (" << rc << "): " << kombgpu_last_error(_ctx) << std::endl;
+        exit(EXIT_FAILURE);
+    }
+
+   public:
+    Kgraph(uint32_t threads, uint64_t readlength, int device, int key_mode)
+        : _threads(threads ? threads : 1), _readlength(readlength), _key_mode(key_mode) {
+        int rc = kombgpu_ctx_create(device, &_ctx);
+        if (rc != KOMBGPU_OK) {
+            std::cerr << "komb2: cannot use CUDA device " << device << ": " << kombgpu_last_error(nullptr) << std::endl;
+            exit(EXIT_FAILURE);
+        }
+        (void)_readlength;  // stored and never read, like the reference (src/graph.cpp:55)
+    }
+    ~Kgraph() {
+        if (_graph) kombgpu_graph_destroy(_graph);
+        if (_ctx) kombgpu_ctx_destroy(_ctx);
+    }
+
+    // Tokenise one SAM file; the mapped file must outlive `hits` (spans point into it).
+    void readSAM(const std::string &samfile, MappedFile &file, HitTable &hits, bool /*fulgor: ignored like the reference*/) {
+        if (!file.open(samfile)) fileNotFoundError(samfile);
+        try {
+            tokenise_sam(file, (int)_threads, hits.tokens, samfile);
+        } catch (const std::exception &e) {
+            std::cerr << e.what() << std::endl;
+            exit(EXIT_FAILURE);
+        }
+    }
+
+    // Both mates are in `hits.tokens` now: intern read keys and unitig names.  The union of the two
+    // mates' unitig sets per read (reference getEdgeInfo) needs no host work: equal keys get equal ids.
+    void getEdgeInfo(HitTable &hits) {
+        const size_t h = hits.tokens.keys.size();
+        InternResult keys = intern_spans(hits.tokens.keys, (int)_threads, false);
+        hits.read_key.swap(keys.ids);
+        // unitig ids: @SQ order first, then first appearance; only unitigs with a hit become vertices
+        std::vector<Span> items;
+        items.reserve(hits.tokens.sq.size() + h);
+        items.insert(items.end(), hits.tokens.sq.begin(), hits.tokens.sq.end());
+        items.insert(items.end(), hits.tokens.rnames.begin(), hits.tokens.rnames.end());
+        const size_t n_sq = hits.tokens.sq.size();
+        InternResult names = intern_spans(items, (int)_threads, true);
+        std::vector<uint8_t> has_hit(names.n_distinct, 0);
+        for (size_t i = n_sq; i < items.size(); ++i) has_hit[names.ids[i]] = 1;
+        std::vector<uint32_t> vid(names.n_distinct, UINT32_MAX);
+        uint32_t next = 0;
+        for (uint32_t d = 0; d < names.n_distinct; ++d)
+            if (has_hit[d]) {
+                vid[d] = next++;
+                const Span &s = items[names.first_index[d]];
+                hits.names.emplace_back(s.p, s.len);
+            }
+        hits.unitig.resize(h);
+#pragma omp parallel for num_threads(_threads) schedule(static)
+        for (size_t i = 0; i < h; ++i) hits.unitig[i] = vid[names.ids[n_sq + i]];
+    }
+
+    void generateGraph(HitTable &hits) {
+        int rc = kombgpu_build_graph(_ctx, hits.read_key.data(), hits.unitig.data(), hits.read_key.size(),
+                                     (uint32_t)hits.names.size(), &_graph);
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_build_graph", rc);
+    }
+
+    void readEdgeList(const std::string &dir, const std::string &inputUnitigs, HitTable &hits) {
+        const std::string edgelist_file = dir + "/edgelist.txt";
+        FILE *ef = fopen(edgelist_file.c_str(), "w");
+        if (ef == nullptr) fileNotFoundError(edgelist_file);
+        auto begin_graph = std::chrono::steady_clock::now();
+        uint32_t n = 0;
+        uint64_t m = 0;
+        kombgpu_graph_counts(_graph, &n, &m);
+        std::vector<uint32_t> u(m), v(m);
+        int rc = kombgpu_graph_edges(_graph, u.data(), v.data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_edges", rc);
+        write_rows(ef, m, 24, (int)_threads, [&](char *p, size_t i) {
+            p = put_u64(p, u[i]); *p++ = '\t';
+            p = put_u64(p, v[i]); *p++ = '\n';
+            return p;
+        });
+        fclose(ef);
+        fprintf(stdout, "\nTime elapsed for initializing igraph graph: %.3f s\n", seconds_since(begin_graph));
+        fprintf(stdout, "\nTime elapsed for simplifying graph: %.3f s\n", 0.0);  // dedup is part of the device build
+        fprintf(stdout, "GraphInfo...\n\tNumber of vertices: %d\n", (int)n);
+        fprintf(stdout, "\tNumber of edges: %d\n", (int)m);
+        // the reference opens and parses the unitig FASTA here and discards the result
+        // (src/graph.cpp:446,565-589): keep its one observable effect, the open check
+        FILE *uf = fopen(inputUnitigs.c_str(), "r");
+        if (uf == nullptr) fileNotFoundError(inputUnitigs);
+        fclose(uf);
+        auto begin_kcore = std::chrono::steady_clock::now();
+        runCore(dir, hits);
+        fprintf(stdout, "\nTime elapsed doing K-core decomposition: %.3f s\n", seconds_since(begin_kcore));
+    }
+
+    void runCore(const std::string &dir, HitTable &hits) {
+        const std::string kcore_file = dir + "/kcore.tsv";
+        const uint32_t n = (uint32_t)hits.names.size();
+        std::vector<int32_t> deg(n), core(n);
+        int rc = kombgpu_degree(_graph, deg.data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_degree", rc);
+        rc = kombgpu_coreness(_graph, core.data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_coreness", rc);
+        FILE *kcf = fopen(kcore_file.c_str(), "w+");
+        if (kcf == nullptr) fileNotFoundError(kcore_file);
+        fprintf(kcf, "#VID\tName\tCoreness\tDegree\n");
+        size_t max_name = 0;
+        for (auto &s : hits.names) max_name = std::max(max_name, s.size());
+        write_rows(kcf, n, max_name + 40, (int)_threads, [&](char *p, size_t i) {
+            p = put_u64(p, i); *p++ = '\t';
+            memcpy(p, hits.names[i].data(), hits.names[i].size()); p += hits.names[i].size(); *p++ = '\t';
+            p = put_u64(p, (uint64_t)core[i]); *p++ = '\t';
+            p = put_u64(p, (uint64_t)deg[i]); *p++ = '\n';
+            return p;
+        });
+        fclose(kcf);
+    }
+
+    void anomalyDetection(const std::string &dir, bool weight) {
+        const uint32_t n = [&] { uint32_t nn = 0; kombgpu_graph_counts(_graph, &nn, nullptr); return nn; }();
+        std::vector<double> score(n);
+        int rc = kombgpu_graph_corea(_graph, _key_mode, score.data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_corea", rc);
+        int32_t max_core = 0;
+        double max_score = 0.0;
+        kombgpu_graph_summary(_graph, &max_core, &max_score);
+        const double dense_ratio = (double)(max_core / 2);  // integer division, like CombineCoreA.h:24
+        fprintf(stdout, "Dense Ratio: %f\n", n ? dense_ratio : 0.0);
+        if (weight) {
+            fprintf(stdout, "Max CoreA score: %f\n", max_score);
+            const std::string anomaly_output = dir + "/CoreA_anomaly.txt";
+            FILE *fp = fopen(anomaly_output.c_str(), "w+");
+            if (fp == nullptr) fileNotFoundError(anomaly_output);
+            write_rows(fp, n, 64, (int)_threads, [&](char *p, size_t i) {
+                p = put_u64(p, i); *p++ = '\t';
+                p += snprintf(p, 48, "%f\n", score[i]);
+                return p;
+            });
+            fclose(fp);
+        }
+        kombgpu_graph_destroy(_graph);
+        _graph = nullptr;
+    }
+
+    const kombgpu_graph *graph() const { return _graph; }
+};
+
+}  // namespace komb
