@@ -5,20 +5,26 @@
 // in HashIndexedMinHeap.h.  Coreness is a unique function of the simple graph,
 // so the result is bit-exact against any correct implementation.
 //
-// One persistent cooperative kernel peels the whole graph:
-//   level k:  SCAN    compact the alive list; vertices with deg == k enter the
-//                     peel queue (ballot/popc warp-aggregated appends)
-//             PROCESS every queued vertex v: for each neighbour u with
-//                     deg[u] > k: atomicSub(deg[u]); the thread that takes it to
-//                     k appends u to the SAME queue (so the level-k cascade
-//                     needs no further grid-wide barrier); a decrement that
-//                     lands below k is undone, so deg[] is clamped at k and the
-//                     final deg[] IS the coreness.
-// The queue is the peel order: each vertex is appended exactly once over the
-// whole run, so it is never reset; CTAs claim chunks from it with a CAS and a
-// level ends when q_done == q_tail.  Empty levels are skipped through a
-// min-reduction of the survivors' degrees done by the scan itself.
+// One persistent cooperative kernel peels the whole graph (PKC-style):
+//   level k:  SCAN     one pass over the compacted alive list: vertices with
+//                      deg == k form the level's frontier list, vertices above k
+//                      are compacted (CTA-wide scan, two global atomics per tile)
+//             PROCESS  the frontier is dealt to the CTAs round-robin; a CTA walks
+//                      its rows edge-parallel: for each neighbour u with
+//                      deg[u] > k: atomicSub(deg[u]); the thread that takes it to
+//                      k owns u and pushes it (ballot/popc aggregated) to the
+//                      CTA's own shared-memory list, processed next by the same
+//                      CTA, so the level-k cascade needs no grid-wide barrier and
+//                      no global queue; a decrement that lands below k is undone,
+//                      so deg[] is clamped at k and the final deg[] IS the coreness.
+//                      Hub rows are cut into slices that all CTAs share in a
+//                      follow-up sub-round.
+// Empty levels are skipped through a min-reduction of the survivors' degrees
+// done by the scan itself.  The peel is bound by its dependency depth (levels x
+// cascade sub-rounds), not by bytes: see DESIGN.md "Peel".
 #include <cooperative_groups.h>
+
+#include <cstdlib>
 
 #include "graph.cuh"
 
@@ -30,28 +36,37 @@ namespace {
 
 constexpr int kPeelThreads = 512;
 constexpr int kPeelWarps = kPeelThreads / 32;
-constexpr uint32_t kSentinel = 0xffffffffu;
-constexpr uint32_t kMaxChunk = 4 * kPeelWarps;               // queue entries one CTA claims at once
-constexpr unsigned long long kWatchdogNs = 10ull * 1000000000ull;  // a wait this long means a broken invariant
+constexpr int kLocalQ = 2048;        // capacity of each CTA-local vertex list (two lists: current, next)
+constexpr int kBatch = 64;           // adjacency ranges one traversal covers
+constexpr int kUnroll = 4;           // independent edge chains per thread (memory-level parallelism)
+constexpr uint32_t kSplit = 4096;    // rows longer than this are cut into slices shared by all CTAs
+constexpr int kSliceLenBits = 20;    // slice entry = first_edge << 20 | length
+constexpr int kScanItems = 8;        // alive-list entries per thread per scan tile
+constexpr int kScanTileV = kPeelThreads * kScanItems;
 
-// Per-round scan results live in three rotating slots: round r uses slot r % 3
-// and CTA 0 re-arms slot (r + 1) % 3 at the start of round r.  That slot was last
-// read right after the grid barrier of round r - 2, and CTA 0 can only be in
-// round r once every CTA has arrived at the barrier of round r - 1, so nobody
-// can still be reading it.  All control-flow decisions are taken from these
-// slots (or from q_done / error at points where they cannot change), never from
-// q_tail, which other CTAs may already be advancing.
+// Per-round results live in three rotating slots: round r uses slot r % 3 and
+// CTA 0 re-arms slot (r + 1) % 3 at the start of round r.  That slot was last
+// read right after a grid barrier of round r - 2, and CTA 0 can only be in
+// round r once every CTA has arrived at the last barrier of round r - 1, so
+// nobody can still be reading it.  All control-flow decisions are taken from
+// these slots at points where they cannot change, so every CTA takes the same
+// path to the same barriers.
 struct PeelState {
-    uint32_t q_tail;        // queue entries appended (monotone, ends at n)
-    uint32_t q_head;        // queue entries claimed
-    uint32_t q_done;        // queue entries fully processed
     uint32_t alive_out[3];  // survivors written by the scan of round r (slot r % 3)
-    uint32_t front_cnt[3];  // vertices that scan put on the queue
+    uint32_t front_cnt[3];  // length of the level's frontier list: scan output + CTA-list overflow
+    uint32_t slice_cnt[3];  // length of the level's slice list (pieces of long rows)
     int32_t next_min[3];    // min degree of the survivors
-    uint32_t error;         // watchdog / invariant flag
+    uint32_t error;
     uint32_t levels;        // non-empty levels
     uint32_t rounds;        // scan phases executed
+    uint32_t subrounds;     // process phases executed (grid-wide)
     int32_t max_core;
+    unsigned long long n_removed;  // vertices peeled (must end at n)
+    unsigned long long overflowed; // discoveries that did not fit a CTA-local list
+    unsigned long long sliced;     // slices published
+    // CTA 0's view of where the time goes (ns): scan, barrier after scan, process, barrier after process
+    unsigned long long prof_ns[4];
+    unsigned long long batches;    // traversals over all CTAs
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -60,76 +75,251 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// Claim protocol.  q_head only moves by atomicAdd, so claims never fail or retry
-// (a CAS loop admits one winner per L2 round trip and serialises the whole
-// level).  A claim made while q_head < q_tail can still overshoot q_tail; the
-// claimer then OWNS slots that are not written yet and waits for them.  A slot
-// is abandoned only when the level is quiescent (q_done == q_tail): every
-// appended entry is processed, nobody can append any more, so the slot cannot
-// fill during this level.  CTA 0 pulls q_head back to q_tail before the next
-// level, which makes abandoned slots claimable again.
+struct BlockShared {
+    uint32_t list[2][kLocalQ];   // current / next CTA-local vertex lists
+    uint32_t next_cnt;           // entries pushed to the next list (may exceed kLocalQ: the excess went global)
+    uint64_t row[kBatch];        // first edge of every range of the batch
+    uint32_t off[kBatch + 1];    // exclusive prefix of the range lengths
+    uint32_t scan[kPeelWarps + 1];
+    uint32_t tile_base[2];       // scan: where this tile's frontier / survivor entries go
+};
+
+// Edge-parallel traversal of the batch described by sh.row / sh.off (kBatch ranges,
+// `total` edges) by the whole CTA: for every neighbour u with deg[u] > k the
+// degree is decremented; the thread whose decrement takes it to k owns u and
+// pushes it to the CTA's next list.  A decrement that lands below k is undone,
+// so deg[] is clamped at k and ends as the coreness.  Every thread keeps kUnroll
+// independent col -> deg -> atomic chains in flight.
+__device__ __forceinline__ void traverse_batch(const uint32_t total, const int32_t k, const uint32_t *__restrict__ col,
+                                               int32_t *deg, uint32_t *next, uint32_t *F, uint32_t *front_cnt,
+                                               BlockShared &sh, uint32_t &overflowed) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
+    for (uint32_t base = 0; base < total; base += kPeelThreads * kUnroll) {
+        uint32_t u[kUnroll];
+        int32_t d[kUnroll];
+        bool push[kUnroll];
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) {
+            const uint32_t e = base + t * kPeelThreads + tid;
+            u[t] = kFullMask;
+            if (e < total) {
+                uint32_t lo_i = 0, hi_i = kBatch;  // off[lo_i] <= e < off[hi_i]
+#pragma unroll
+                for (int sgm = 0; sgm < 6; ++sgm) {
+                    const uint32_t mid = (lo_i + hi_i) >> 1;
+                    if (sh.off[mid] <= e) lo_i = mid; else hi_i = mid;
+                }
+                u[t] = col[sh.row[lo_i] + (e - sh.off[lo_i])];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? __ldcg(&deg[u[t]]) : INT32_MIN;
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) {
+            push[t] = false;
+            if (d[t] > k) {
+                const int32_t old = atomicSub(&deg[u[t]], 1);
+                if (old == k + 1) push[t] = true;             // u just reached level k: ours to peel
+                else if (old <= k) atomicAdd(&deg[u[t]], 1);  // already at level k: undo (clamp)
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) {
+            const uint32_t pm = __ballot_sync(kFullMask, push[t]);
+            if (pm == 0) continue;
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(&sh.next_cnt, (uint32_t)__popc(pm));
+            pos = __shfl_sync(kFullMask, pos, 0) + __popc(pm & lanemask_lt());
+            if (push[t]) {
+                if (pos < kLocalQ) next[pos] = u[t];
+                else { F[atomicAdd(front_cnt, 1u)] = u[t]; ++overflowed; }  // rare: the next sub-round takes it
+            }
+        }
+    }
+}
+
+// PROCESS phase of one sub-round for one CTA (PKC-style, CTA-local cascade).
+//
+// Work of a sub-round: the slice list S[s_lo, s_hi) (pieces of long rows) and the
+// frontier list F[f_lo, f_hi) (vertices from the scan, or overflow of an earlier
+// sub-round).  Both are dealt to the CTAs round-robin: no claiming, no atomics.
+// A CTA traverses a batch of ranges edge-parallel with all its threads.
+// Vertices it discovers go to its own shared-memory "next" list and are
+// processed by the same CTA right after the current list: a cascade chain costs
+// row_ptr -> col -> deg -> atomic round trips and a few CTA barriers per step,
+// and never touches a global queue or waits for another CTA.  A row longer than
+// kSplit is not traversed by the CTA that meets it: it is cut into slices
+// appended to S for the next sub-round, so a hub is shared by the whole grid.
+// What does not fit the shared-memory list is appended to F for the next
+// sub-round as well.
+__device__ __forceinline__ uint32_t process_subround(const int32_t k, uint32_t *F, const uint32_t f_lo, const uint32_t f_hi,
+                                                     uint32_t *front_cnt, uint64_t *S, const uint32_t s_lo,
+                                                     const uint32_t s_hi, uint32_t *slice_cnt,
+                                                     const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                                                     int32_t *deg, PeelState *st, BlockShared &sh) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
+    uint32_t cur = 0;  // index of the current list
+    uint32_t removed = 0, batches = 0, overflowed = 0, sliced = 0;
+    if (tid == 0) sh.next_cnt = 0;
+    __syncthreads();
+
+    // ---- slices: kBatch of them per traversal, dealt round-robin ----
+    const uint32_t n_slices = s_hi - s_lo;
+    for (uint32_t g0 = blockIdx.x * kBatch; g0 < n_slices; g0 += gridDim.x * kBatch) {
+        uint32_t my_len = 0;
+        uint64_t my_row = 0;
+        if (tid < kBatch && g0 + tid < n_slices) {
+            const uint64_t e = __ldcg(&S[s_lo + g0 + tid]);
+            my_row = e >> kSliceLenBits;
+            my_len = (uint32_t)(e & ((1u << kSliceLenBits) - 1));
+        }
+        uint32_t total = 0;
+        const uint32_t ex = block_excl_scan_add<uint32_t, kPeelThreads>(my_len, sh.scan, &total);
+        if (tid < kBatch) { sh.off[tid] = ex; sh.row[tid] = my_row; }
+        if (tid == 0) sh.off[kBatch] = total;
+        __syncthreads();
+        ++batches;
+        traverse_batch(total, k, col, deg, sh.list[cur ^ 1], F, front_cnt, sh, overflowed);
+        __syncthreads();
+    }
+
+    // ---- vertices: own discoveries first, then the CTA's share of the frontier list ----
+    const uint32_t n_front = f_hi - f_lo;
+    const uint32_t chunk_sz = min((uint32_t)kBatch, max(1u, (n_front + gridDim.x - 1) / gridDim.x));
+    const uint32_t n_chunks = (n_front + chunk_sz - 1) / chunk_sz;
+    // start dealing where the slices stopped, so that CTA 0 does not get the first share of both
+    uint32_t chunk = (blockIdx.x + gridDim.x - (n_slices / kBatch) % gridDim.x) % gridDim.x;
+    while (true) {
+        uint32_t n_cur = min(sh.next_cnt, (uint32_t)kLocalQ);
+        __syncthreads();  // everyone has read next_cnt
+        if (n_cur > 0) {
+            cur ^= 1;     // discoveries first: they are the critical path of the cascade
+            if (tid == 0) sh.next_cnt = 0;
+        } else if (chunk < n_chunks) {
+            const uint32_t b = f_lo + chunk * chunk_sz;
+            n_cur = min(chunk_sz, f_hi - b);
+            if (tid < n_cur) sh.list[cur][tid] = __ldcg(&F[b + tid]);  // F is rewritten every level: skip L1
+            chunk += gridDim.x;
+        } else {
+            break;
+        }
+        __syncthreads();
+        const uint32_t *list = sh.list[cur];
+        for (uint32_t b0 = 0; b0 < n_cur; b0 += kBatch) {
+            const uint32_t m = min((uint32_t)kBatch, n_cur - b0);
+            uint32_t my_len = 0;
+            uint64_t my_row = 0;
+            if (tid < m) {
+                const uint32_t v = list[b0 + tid];
+                my_row = row_ptr[v];
+                my_len = (uint32_t)(row_ptr[v + 1] - my_row);
+                if (my_len > kSplit) {
+                    // hub row: hand it to the whole grid as slices of the next sub-round
+                    const uint32_t n_sl = (my_len + kSplit - 1) / kSplit;
+                    const uint32_t s0 = atomicAdd(slice_cnt, n_sl);
+                    for (uint32_t i = 0; i < n_sl; ++i)
+                        S[s0 + i] = ((my_row + (uint64_t)i * kSplit) << kSliceLenBits) | min(kSplit, my_len - i * kSplit);
+                    sliced += n_sl;
+                    my_len = 0;
+                }
+            }
+            uint32_t total = 0;
+            const uint32_t ex = block_excl_scan_add<uint32_t, kPeelThreads>(my_len, sh.scan, &total);
+            if (tid < kBatch) { sh.off[tid] = ex; sh.row[tid] = my_row; }
+            if (tid == 0) sh.off[kBatch] = total;
+            __syncthreads();
+            ++batches;
+            traverse_batch(total, k, col, deg, sh.list[cur ^ 1], F, front_cnt, sh, overflowed);
+            __syncthreads();  // row/off are reused by the next batch; next_cnt is complete
+        }
+        removed += n_cur;
+    }
+    overflowed = warp_reduce_add(overflowed);
+    sliced = warp_reduce_add(sliced);
+    if (lane == 0 && overflowed) atomicAdd(&st->overflowed, (unsigned long long)overflowed);
+    if (lane == 0 && sliced) atomicAdd(&st->sliced, (unsigned long long)sliced);
+    if (tid == 0 && batches) atomicAdd(&st->batches, (unsigned long long)batches);
+    return removed;
+}
+
 __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const uint64_t *__restrict__ row_ptr,
                                                             const uint32_t *__restrict__ col, int32_t *deg,
-                                                            uint32_t *queue, uint32_t *alive_a, uint32_t *alive_b,
+                                                            uint32_t *F, uint64_t *S, uint32_t *alive_a, uint32_t *alive_b,
                                                             PeelState *st) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ uint32_t s_begin, s_cnt;
-    __shared__ uint64_t s_row[kMaxChunk];      // first edge of each claimed vertex
-    __shared__ uint32_t s_off[kMaxChunk + 1];  // exclusive prefix of their row lengths
-    __shared__ uint32_t s_scan[kPeelWarps + 1];
-    const uint32_t lane = lane_id();
-    const uint32_t warp_in_block = threadIdx.x >> 5;
-    const uint64_t warp_global = (uint64_t)blockIdx.x * kPeelWarps + warp_in_block;
-    const uint64_t warps_total = (uint64_t)gridDim.x * kPeelWarps;
+    __shared__ BlockShared sh;
+    const uint32_t tid = threadIdx.x, lane = lane_id();
 
     int32_t k = 0;
     uint32_t n_alive = n;
     const uint32_t *alive_src = nullptr;  // nullptr = identity (every vertex)
     uint32_t *alive_dst = alive_a;
     uint32_t round = 0;
+    uint32_t removed = 0;                 // vertices this CTA peeled
 
     while (true) {
         const uint32_t par = round % 3;
         // ---------------- SCAN ----------------
-        if (blockIdx.x == 0 && threadIdx.x == 0) {  // re-arm the slot of the NEXT round
+        // One pass over the alive list: vertices at deg == k go to the frontier list F,
+        // vertices above k are compacted into the next alive list, the rest (peeled at an
+        // earlier level) are dropped.  Tiles of kScanTileV entries; positions come from a
+        // CTA-wide scan, so each tile costs two global atomics in all.
+        if (blockIdx.x == 0 && tid == 0) {  // re-arm the slot of the NEXT round
             const uint32_t nxt = (round + 1) % 3;
             st->alive_out[nxt] = 0;
             st->front_cnt[nxt] = 0;
+            st->slice_cnt[nxt] = 0;
             st->next_min[nxt] = INT32_MAX;
             st->rounds = round + 1;
         }
+        const bool prof = (blockIdx.x == 0 && tid == 0);
+        unsigned long long tp0 = prof ? global_ns() : 0;
         int32_t local_min = INT32_MAX;
-        for (uint64_t base = warp_global * 32; base < n_alive; base += warps_total * 32) {
-            const uint64_t i = base + lane;
-            bool front = false, surv = false;
-            uint32_t v = 0;
-            if (i < n_alive) {
-                v = alive_src ? alive_src[i] : (uint32_t)i;
-                const int32_t d = __ldcg(&deg[v]);
-                front = (d == k);
-                surv = (d > k);  // d < k: peeled at an earlier level, drop from the list
-                if (surv) local_min = min(local_min, d);
+        for (uint64_t tile = (uint64_t)blockIdx.x * kScanTileV; tile < n_alive; tile += (uint64_t)gridDim.x * kScanTileV) {
+            uint32_t v[kScanItems];
+            uint32_t flag[kScanItems];  // 1 = frontier, 0x10000 = survivor
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < kScanItems; ++j) {
+                const uint64_t i = tile + (uint64_t)j * kPeelThreads + tid;
+                flag[j] = 0;
+                v[j] = 0;
+                if (i < n_alive) v[j] = alive_src ? __ldcg(&alive_src[i]) : (uint32_t)i;  // rewritten every round: skip L1
             }
-            const uint32_t fm = __ballot_sync(kFullMask, front);
-            const uint32_t sm = __ballot_sync(kFullMask, surv);
-            uint32_t fbase = 0, sbase = 0;
-            if (lane == 0) {
-                if (fm) {
-                    fbase = atomicAdd(&st->q_tail, (uint32_t)__popc(fm));
-                    atomicAdd(&st->front_cnt[par], (uint32_t)__popc(fm));
+#pragma unroll
+            for (int j = 0; j < kScanItems; ++j) {
+                const uint64_t i = tile + (uint64_t)j * kPeelThreads + tid;
+                if (i < n_alive) {
+                    const int32_t d = __ldcg(&deg[v[j]]);
+                    if (d == k) flag[j] = 1u;
+                    else if (d > k) { flag[j] = 0x10000u; local_min = min(local_min, d); }
                 }
-                if (sm) sbase = atomicAdd(&st->alive_out[par], (uint32_t)__popc(sm));
+                mine += flag[j];
             }
-            fbase = __shfl_sync(kFullMask, fbase, 0);
-            sbase = __shfl_sync(kFullMask, sbase, 0);
-            if (front) queue[fbase + __popc(fm & lanemask_lt())] = v;
-            if (surv) alive_dst[sbase + __popc(sm & lanemask_lt())] = v;
+            uint32_t total = 0;
+            uint32_t ex = block_excl_scan_add<uint32_t, kPeelThreads>(mine, sh.scan, &total);  // both counts: 16 bits each
+            if (tid == 0) {
+                const uint32_t nf = total & 0xffffu, ns = total >> 16;
+                sh.tile_base[0] = nf ? atomicAdd(&st->front_cnt[par], nf) : 0;
+                sh.tile_base[1] = ns ? atomicAdd(&st->alive_out[par], ns) : 0;
+            }
+            __syncthreads();
+            uint32_t fpos = sh.tile_base[0] + (ex & 0xffffu), spos = sh.tile_base[1] + (ex >> 16);
+#pragma unroll
+            for (int j = 0; j < kScanItems; ++j) {
+                if (flag[j] == 1u) F[fpos++] = v[j];
+                else if (flag[j]) alive_dst[spos++] = v[j];
+            }
+            __syncthreads();  // tile_base is reused by the next tile
         }
         local_min = warp_reduce_min(local_min);
         if (lane == 0 && local_min != INT32_MAX) atomicMin(&st->next_min[par], local_min);
+        unsigned long long tp1 = prof ? global_ns() : 0;
         grid.sync();
+        unsigned long long tp2 = prof ? global_ns() : 0;
+        if (prof) { st->prof_ns[0] += tp1 - tp0; st->prof_ns[1] += tp2 - tp1; }
 
-        const uint32_t front_cnt = __ldcg(&st->front_cnt[par]);
+        uint32_t front_hi = __ldcg(&st->front_cnt[par]);
         const uint32_t survivors = __ldcg(&st->alive_out[par]);
         const int32_t min_next = __ldcg(&st->next_min[par]);
         // the compacted list becomes the next scan's input
@@ -138,132 +328,36 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         n_alive = survivors;
         ++round;
 
-        if (front_cnt == 0) {
+        if (front_hi == 0) {
             // empty level: nothing to process; jump to the smallest remaining degree
             if (survivors == 0 || min_next == INT32_MAX) break;
             k = min_next;
             continue;
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (blockIdx.x == 0 && tid == 0) {
             st->levels += 1;
             st->max_core = k;
         }
 
         // ---------------- PROCESS ----------------
-        // Thread i of the CTA owns queue slot s_begin + i of the current claim and keeps
-        // it `pending` until that slot has been written AND processed.
-        bool pending = false;
-        uint32_t my_slot = 0;
-        unsigned long long idle_since = 0;
-        while (true) {
-            if (__syncthreads_count(pending) == 0) {
-                if (threadIdx.x == 0) {
-                    uint32_t begin = 0, cnt = 0;
-                    while (true) {
-                        const uint32_t h = ld_volatile_u32(&st->q_head);
-                        const uint32_t t = ld_volatile_u32(&st->q_tail);
-                        if (h < t) {
-                            uint32_t take = (t - h + gridDim.x - 1) / gridDim.x;
-                            take = min(max(take, 1u), kMaxChunk);
-                            begin = atomicAdd(&st->q_head, take);
-                            cnt = begin < n ? min(take, n - begin) : 0;
-                            if (cnt) break;
-                            continue;
-                        }
-                        // nothing to claim: the level is over once everything appended is processed
-                        const uint32_t d = ld_volatile_u32(&st->q_done);
-                        const uint32_t t2 = ld_volatile_u32(&st->q_tail);
-                        if (d == t2 || ld_volatile_u32(&st->error)) break;
-                        if (idle_since == 0) idle_since = global_ns();
-                        else if (global_ns() - idle_since > kWatchdogNs) { atomicExch(&st->error, 1u); break; }
-                        __nanosleep(32);
-                    }
-                    s_begin = begin;
-                    s_cnt = cnt;
-                }
-                __syncthreads();
-                if (s_cnt == 0) break;  // level over
-                if (threadIdx.x < s_cnt) { pending = true; my_slot = s_begin + threadIdx.x; }
-            }
-            // poll the owned slots once; rows that are there get processed now
-            bool ready = false;
-            uint32_t my_len = 0;
-            uint64_t my_row = 0;
-            if (pending) {
-                const uint32_t v = ld_volatile_u32(&queue[my_slot]);
-                if (v != kSentinel) {
-                    ready = true;
-                    my_row = row_ptr[v];
-                    my_len = (uint32_t)(row_ptr[v + 1] - my_row);
-                }
-            }
-            uint32_t total = 0;
-            const uint32_t ex = block_excl_scan_add<uint32_t, kPeelThreads>(my_len, s_scan, &total);
-            if (threadIdx.x < kMaxChunk) { s_off[threadIdx.x] = ex; s_row[threadIdx.x] = my_row; }
-            if (threadIdx.x == 0) s_off[kMaxChunk] = total;
-            const int n_ready = __syncthreads_count(ready);  // also publishes s_off / s_row
-            if (n_ready == 0) {
-                // owned slots still empty: give them up only when the level is quiescent
-                if (threadIdx.x == 0) {
-                    const uint32_t d = ld_volatile_u32(&st->q_done);
-                    const uint32_t t2 = ld_volatile_u32(&st->q_tail);
-                    uint32_t over = (d == t2 || ld_volatile_u32(&st->error)) ? 1u : 0u;
-                    if (!over) {
-                        if (idle_since == 0) idle_since = global_ns();
-                        else if (global_ns() - idle_since > kWatchdogNs) { atomicExch(&st->error, 2u); over = 1u; }
-                        __nanosleep(32);
-                    }
-                    s_cnt = over;
-                }
-                __syncthreads();
-                if (s_cnt) break;  // level over (pending slots stay unwritten this level)
-                continue;
-            }
-            idle_since = 0;
-
-            // block-wide edge-parallel traversal of the ready rows
-            for (uint32_t base = warp_in_block * 32; base < total; base += kPeelThreads) {
-                const uint32_t j = base + lane;
-                bool push = false;
-                uint32_t u = 0;
-                if (j < total) {
-                    uint32_t lo = 0, hi = kMaxChunk;  // s_off[lo] <= j < s_off[hi]
-                    while (hi - lo > 1) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (s_off[mid] <= j) lo = mid; else hi = mid;
-                    }
-                    u = col[s_row[lo] + (j - s_off[lo])];
-                    if (__ldcg(&deg[u]) > k) {
-                        const int32_t old = atomicSub(&deg[u], 1);
-                        if (old == k + 1) push = true;             // u just reached level k: ours to enqueue
-                        else if (old <= k) atomicAdd(&deg[u], 1);  // already at level k: undo (clamp)
-                    }
-                }
-                const uint32_t pm = __ballot_sync(kFullMask, push);
-                if (pm) {
-                    uint32_t slot = 0;
-                    if (lane == 0) slot = atomicAdd(&st->q_tail, (uint32_t)__popc(pm));
-                    slot = __shfl_sync(kFullMask, slot, 0);
-                    if (push) {
-                        volatile uint32_t *q = queue;  // consumers poll the slot leaving the sentinel value
-                        q[slot + __popc(pm & lanemask_lt())] = u;
-                    }
-                }
-            }
-            if (ready) pending = false;
-            __syncthreads();  // every decrement of this batch is issued before it counts as done
-            if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(&st->q_done, (uint32_t)n_ready);
-            }
+        // sub-round 0 takes the scan's frontier; later ones take the slices of long rows and
+        // whatever overflowed the CTA-local lists
+        uint32_t front_lo = 0, slice_lo = 0, slice_hi = 0;
+        while (front_lo < front_hi || slice_lo < slice_hi) {
+            removed += process_subround(k, F, front_lo, front_hi, &st->front_cnt[par], S, slice_lo, slice_hi,
+                                        &st->slice_cnt[par], row_ptr, col, deg, st, sh);
+            unsigned long long tp3 = prof ? global_ns() : 0;
+            if (prof) st->subrounds += 1;
+            grid.sync();
+            if (prof) { st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += global_ns() - tp3; tp2 = global_ns(); }
+            front_lo = front_hi;
+            slice_lo = slice_hi;
+            front_hi = __ldcg(&st->front_cnt[par]);  // stable: nothing appends between sub-rounds
+            slice_hi = __ldcg(&st->slice_cnt[par]);
         }
-        grid.sync();
-        // q_done == q_tail here and neither moves until the next PROCESS phase
-        const uint32_t done = __ldcg(&st->q_done);
-        if (done >= n || __ldcg(&st->error)) break;
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->q_head = done;  // un-claim overshoot / abandoned slots
         k += 1;
     }
+    if (tid == 0 && removed) atomicAdd(&st->n_removed, (unsigned long long)removed);
 }
 
 }  // namespace
@@ -281,28 +375,35 @@ int peel_coreness(kombgpu_graph *g) {
     if (n == 0) { g->has_core = true; return KOMBGPU_OK; }
     KG_CUDA(ctx, cudaMemcpyAsync(g->core, g->deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
 
-    DevBuf<uint32_t> queue, alive_a, alive_b;
-    DevBuf<PeelState> state(ctx, 1);
-    KG_ALLOC(ctx, queue, n);
-    KG_ALLOC(ctx, alive_a, n);
-    KG_ALLOC(ctx, alive_b, n);
-    if (!state) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_CUDA(ctx, cudaMemsetAsync(queue.p, 0xff, (size_t)n * sizeof(uint32_t), ctx->stream));
-    PeelState init{};
-    for (int i = 0; i < 3; ++i) init.next_min[i] = INT32_MAX;
-    KG_CUDA(ctx, cudaMemcpyAsync(state.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-
     int per_sm = 0;
     KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel, kPeelThreads, 0));
     if (per_sm < 1) return ctx_fail(ctx, KOMBGPU_ECUDA, "peel kernel does not fit on an SM");
     const int grid = per_sm * ctx->sm_count;  // persistent: every CTA resident (cooperative launch)
+
+    DevBuf<uint32_t> frontier, alive_a, alive_b;
+    DevBuf<uint64_t> slices;
+    DevBuf<PeelState> state(ctx, 1);
+    // a row is sliced at most once: <= 2E/kSplit long rows, each giving <= len/kSplit + 1 slices
+    const uint64_t slice_cap = 4 * g->n_edges / kSplit + 64;
+    if (slice_cap >= 0xffffffffull || 2 * g->n_edges >= (1ull << (64 - kSliceLenBits)))
+        return ctx_fail(ctx, KOMBGPU_EINVAL, "graph too large for the slice encoding");
+    KG_ALLOC(ctx, slices, slice_cap);
+    KG_ALLOC(ctx, frontier, n);   // every vertex enters a frontier list at most once
+    KG_ALLOC(ctx, alive_a, n);
+    KG_ALLOC(ctx, alive_b, n);
+    if (!state) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    PeelState init{};
+    for (int i = 0; i < 3; ++i) init.next_min[i] = INT32_MAX;
+    KG_CUDA(ctx, cudaMemcpyAsync(state.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+
     uint32_t n_arg = n;
     const uint64_t *row_ptr = g->row_ptr;
     const uint32_t *col = g->col;
     int32_t *core = g->core;
-    uint32_t *q = queue.p, *aa = alive_a.p, *ab = alive_b.p;
+    uint32_t *fr = frontier.p, *aa = alive_a.p, *ab = alive_b.p;
+    uint64_t *sl = slices.p;
     PeelState *sp = state.p;
-    void *args[] = {&n_arg, &row_ptr, &col, &core, &q, &aa, &ab, &sp};
+    void *args[] = {&n_arg, &row_ptr, &col, &core, &fr, &sl, &aa, &ab, &sp};
     cudaEvent_t ev0, ev1;
     KG_CUDA(ctx, cudaEventCreate(&ev0));
     KG_CUDA(ctx, cudaEventCreate(&ev1));
@@ -318,11 +419,15 @@ int peel_coreness(kombgpu_graph *g) {
 
     PeelState fin{};
     KG_TRY(read_back(ctx, state.p, &fin, 1));
-    if (fin.error) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel watchdog tripped (code %u, tail %u of %u)", fin.error, fin.q_tail, n);
-    if (fin.q_tail != n) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel ended with %u of %u vertices queued", fin.q_tail, n);
+    if (getenv("KOMBGPU_DEBUG"))
+        fprintf(stderr, "[kombgpu] peel n=%u levels=%u rounds=%u subrounds=%u grid=%d kernel=%.3f ms | cta0: scan %.3f ms, sync1 %.3f ms, process %.3f ms, sync2 %.3f ms | batches %llu overflow %llu slices %llu\n",
+                n, fin.levels, fin.rounds, fin.subrounds, grid, g->st.ms_peel_kernel, fin.prof_ns[0] * 1e-6, fin.prof_ns[1] * 1e-6,
+                fin.prof_ns[2] * 1e-6, fin.prof_ns[3] * 1e-6, fin.batches, fin.overflowed, fin.sliced);
+    if (fin.error) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel invariant broken (code %u, %llu of %u vertices peeled)", fin.error, fin.n_removed, n);
+    if (fin.n_removed != n) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel ended with %llu of %u vertices peeled", fin.n_removed, n);
     g->st.max_coreness = fin.max_core;
     g->st.peel_levels = fin.levels;
-    g->st.peel_rounds = fin.rounds;
+    g->st.peel_rounds = fin.rounds + fin.subrounds;
     g->has_core = true;
     return KOMBGPU_OK;
 }
