@@ -162,6 +162,70 @@ int kombgpu_graph_device_arrays(const kombgpu_graph *g, const uint64_t **row_ptr
                                 const uint64_t **edges_packed, const int32_t **degree,
                                 const int32_t **coreness, const double **score);
 
+/* ---- multi-GPU: one rank's share of a graph partitioned by unitig-id range --------
+ *
+ * One process per GPU; the exchanges between the calls below are done by the host
+ * (torch.distributed / NCCL in komb_b200/distributed.py, MPI or ncclSend/Recv in
+ * a C++ host).  `bounds[0..n_parts]` are the vertex-range boundaries: rank j owns
+ * unitig ids [bounds[j], bounds[j+1]).  All pointers in this section whose name
+ * ends in _dev are device pointers; counts and scalars are host pointers.
+ *
+ *   stage 1  every rank: its reads' hits -> local simple edge set  (kombgpu_local_edges_dev)
+ *            route both directions of every edge to the owner of the source
+ *            (kombgpu_edgeset_route_dev) -> all-to-all -> kombgpu_part_build_dev
+ *   stage 2  per level k: kombgpu_part_peel_scan; then sub-rounds of
+ *            kombgpu_part_peel_process (local cascade, remote targets to the outbox)
+ *            -> kombgpu_part_outbox_route_dev -> all-to-all -> kombgpu_part_peel_apply_dev
+ *            until no rank has a frontier or an outbox entry left
+ *   stage 3  all-gather (coreness, degree) -> kombgpu_corea_dev
+ */
+typedef struct kombgpu_edgeset kombgpu_edgeset;
+typedef struct kombgpu_part kombgpu_part;
+
+/* Hits of this rank's reads (global unitig ids) -> sorted unique simple edges, kept
+ * on the device.  Same semantics as kombgpu_build_graph up to the edge list. */
+int kombgpu_local_edges_dev(kombgpu_ctx *ctx, const uint32_t *read_key_dev, const uint32_t *unitig_dev,
+                            uint64_t n_hits, uint32_t n_vertices_global, kombgpu_edgeset **out);
+/* The same from arbitrary (u, v) pairs (R-MAT style inputs). */
+int kombgpu_edgeset_from_pairs_dev(kombgpu_ctx *ctx, const uint32_t *u_dev, const uint32_t *v_dev, uint64_t n_pairs,
+                                   uint32_t n_vertices_global, kombgpu_edgeset **out);
+int kombgpu_edgeset_counts(const kombgpu_edgeset *es, uint64_t *n_edges, uint64_t *n_pairs, uint64_t *n_unique_hits);
+/* Directed entries (src << 32 | dst), both directions of every local edge, grouped
+ * by the owner of src.  send_dev holds 2 * n_edges entries; counts[n_parts]. */
+int kombgpu_edgeset_route_dev(kombgpu_edgeset *es, const uint32_t *bounds, int n_parts, uint64_t *send_dev,
+                              uint64_t *counts);
+void kombgpu_edgeset_destroy(kombgpu_edgeset *es);
+
+/* Received directed entries with src in [v_lo, v_hi) (duplicates allowed: the same
+ * edge may have been seen by several ranks) -> this rank's CSR rows. */
+int kombgpu_part_build_dev(kombgpu_ctx *ctx, const uint64_t *entries_dev, uint64_t count, uint32_t v_lo,
+                           uint32_t v_hi, uint32_t n_vertices_global, kombgpu_part **out);
+void kombgpu_part_destroy(kombgpu_part *part);
+int kombgpu_part_counts(const kombgpu_part *part, uint32_t *n_local, uint64_t *n_directed, int32_t *max_degree);
+/* row_ptr[n_local+1], col[n_directed] (global ids), degree[n_local], coreness[n_local]
+ * (working degrees during the peel, the coreness once it ended). */
+int kombgpu_part_device_arrays(const kombgpu_part *part, const uint64_t **row_ptr, const uint32_t **col,
+                               const int32_t **degree, const int32_t **coreness);
+
+int kombgpu_part_peel_begin(kombgpu_part *part);
+/* Level k: compact the local alive list; n_front local vertices at degree k,
+ * n_alive above it, min_next = smallest degree above k (INT32_MAX if none). */
+int kombgpu_part_peel_scan(kombgpu_part *part, int32_t k, uint32_t *n_front, uint32_t *n_alive, int32_t *min_next);
+/* Peel the local frontier of level k including its local cascade; decrements of
+ * vertices other ranks own are collected in the outbox (*n_outbox entries). */
+int kombgpu_part_peel_process(kombgpu_part *part, int32_t k, uint32_t *n_outbox);
+/* Outbox grouped by owner: send_dev holds n_outbox global ids; counts[n_parts]. */
+int kombgpu_part_outbox_route_dev(kombgpu_part *part, const uint32_t *bounds, int n_parts, uint32_t *send_dev,
+                                  uint64_t *counts);
+/* Apply received decrements (global ids of vertices this rank owns); vertices that
+ * reach degree k form the new local frontier (*n_front). */
+int kombgpu_part_peel_apply_dev(kombgpu_part *part, int32_t k, const uint32_t *recv_dev, uint64_t count,
+                                uint32_t *n_front);
+
+/* kombgpu_corea on device arrays (score_dev[n]); *max_score on the host. */
+int kombgpu_corea_dev(kombgpu_ctx *ctx, const int32_t *coreness_dev, const int32_t *degree_dev, uint32_t n,
+                      int key_mode, double *score_dev, double *max_score);
+
 int kombgpu_abi_version(void);
 
 #ifdef __cplusplus

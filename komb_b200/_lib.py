@@ -56,6 +56,22 @@ SIGNATURES = {
     "kombgpu_graph_analyse": (c_int, [c_void_p, c_int]),
     "kombgpu_graph_stats": (c_int, [c_void_p, POINTER(Stats)]),
     "kombgpu_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
+    # multi-GPU partition interface
+    "kombgpu_local_edges_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_edgeset_from_pairs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_edgeset_counts": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]),
+    "kombgpu_edgeset_route_dev": (c_int, [c_void_p, POINTER(c_uint32), c_int, c_void_p, POINTER(c_uint64)]),
+    "kombgpu_edgeset_destroy": (None, [c_void_p]),
+    "kombgpu_part_build_dev": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_part_destroy": (None, [c_void_p]),
+    "kombgpu_part_counts": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32)]),
+    "kombgpu_part_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 4),
+    "kombgpu_part_peel_begin": (c_int, [c_void_p]),
+    "kombgpu_part_peel_scan": (c_int, [c_void_p, c_int32, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_int32)]),
+    "kombgpu_part_peel_process": (c_int, [c_void_p, c_int32, POINTER(c_uint32)]),
+    "kombgpu_part_outbox_route_dev": (c_int, [c_void_p, POINTER(c_uint32), c_int, c_void_p, POINTER(c_uint64)]),
+    "kombgpu_part_peel_apply_dev": (c_int, [c_void_p, c_int32, c_void_p, c_uint64, POINTER(c_uint32)]),
+    "kombgpu_corea_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p, POINTER(c_double)]),
 }
 
 _lib = None

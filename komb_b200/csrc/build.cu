@@ -236,96 +236,60 @@ __global__ void __launch_bounds__(kThreads) fill_col_kernel(const uint64_t *__re
 
 __global__ void set_u64_kernel(uint64_t *p, uint64_t v) { *p = v; }
 
-// sorted (loops possible) pair keys -> g->edges / CSR.  `keys` has `count` entries.
-int finish_graph(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, uint32_t n, kombgpu_graph *g) {
-    const int bn = bits_for(n > 0 ? n - 1 : 0);
-    // unique + loop drop
-    DevBuf<uint32_t> d_count(ctx, 1);
-    if (!d_count) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    DevBuf<uint64_t> edges;
-    KG_ALLOC(ctx, edges, count);
-    KG_TRY((device_scan<uint32_t>(ctx, count, EdgeFlagIn{keys}, CompactKeysU64{keys, edges.p}, d_count.p)));
-    uint32_t n_edges32 = 0;
-    KG_TRY(read_back(ctx, d_count.p, &n_edges32, 1));
-    const uint64_t E = n_edges32;
-    g->n = n;
-    g->n_edges = E;
-    g->st.n_edges = E;
-    g->st.n_vertices = n;
-
-    // backward half: (v << 32 | u) stably sorted by v
-    DevBuf<uint64_t> sw_a, sw_b;
-    KG_ALLOC(ctx, sw_a, E);
-    KG_ALLOC(ctx, sw_b, E);
-    uint64_t *swapped = sw_a.p;
-    if (E) {
-        KG_LAUNCH(ctx, swap_pack_kernel, min(grid_for(E, kThreads), 148u * 16u), kThreads, 0, edges.p, E, sw_a.p);
-        RadixPass passes[8];
-        int np = plan_radix_passes(32, 32 + bn, 0, 0, passes);
-        KG_TRY(radix_sort_u64(ctx, sw_a.p, sw_b.p, E, passes, np, &swapped));
+// keys sorted by high word: idx[j] = first position whose high word is >= bounds[j]
+__global__ void lower_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t count, const uint32_t *__restrict__ bounds,
+                                    int nb, uint64_t *__restrict__ idx) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    const uint64_t target = (uint64_t)bounds[j] << 32;
+    uint64_t lo = 0, hi = count;  // first position with keys[pos] >= target
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (keys[mid] < target) lo = mid + 1; else hi = mid;
     }
-    DevBuf<uint32_t> fwd_start, back_start;
-    KG_ALLOC(ctx, fwd_start, (size_t)n + 1);
-    KG_ALLOC(ctx, back_start, (size_t)n + 1);
-    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, edges.p, E, n, fwd_start.p);
-    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, swapped, E, n, back_start.p);
-
-    DevBuf<uint64_t> row_ptr;
-    DevBuf<int32_t> deg, max_deg(ctx, 1);
-    DevBuf<uint32_t> col;
-    KG_ALLOC(ctx, row_ptr, (size_t)n + 1);
-    KG_ALLOC(ctx, deg, n);
-    KG_ALLOC(ctx, col, 2 * E);
-    if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
-    KG_TRY((device_scan<uint64_t>(ctx, n, DegreeIn{fwd_start.p, back_start.p}, DegreeOut{row_ptr.p, deg.p},
-                                  (uint64_t *)nullptr)));
-    if (n) KG_LAUNCH(ctx, reduce_max_i32_kernel, min(grid_for(n, kThreads), 148u * 8u), kThreads, 0, deg.p, (uint64_t)n, max_deg.p);
-    KG_LAUNCH(ctx, set_u64_kernel, 1, 1, 0, row_ptr.p + n, 2 * E);
-    if (E)
-        KG_LAUNCH(ctx, fill_col_kernel, min(grid_for(E, kThreads), 148u * 16u), kThreads, 0, edges.p, swapped, E, row_ptr.p,
-                  fwd_start.p, back_start.p, col.p);
-    KG_TRY(read_back(ctx, max_deg.p, &g->st.max_degree, 1));
-
-    g->edges = edges.take();
-    g->row_ptr = row_ptr.take();
-    g->col = col.take();
-    g->deg = deg.take();
-    return KOMBGPU_OK;
+    idx[j] = lo;
 }
 
-}  // namespace
-
-int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
-                     kombgpu_graph *g) {
-    if (n_pairs >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_pairs >= 2^32 is not supported on one device");
-    const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
-    DevBuf<uint64_t> ka, kb;
-    DevBuf<uint32_t> info(ctx, 2);
-    KG_ALLOC(ctx, ka, n_pairs);
-    KG_ALLOC(ctx, kb, n_pairs);
-    if (!info) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_CUDA(ctx, cudaMemsetAsync(info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
-    uint64_t *sorted = ka.p;
-    if (n_pairs) {
-        KG_LAUNCH(ctx, pack_pairs_kernel, min(grid_for(n_pairs, kThreads), 148u * 16u), kThreads, 0, u, v, n_pairs, n_vertices,
-                  ka.p, info.p);
-        RadixPass passes[8];
-        int np = plan_radix_passes(0, bn, 32, 32 + bn, passes);
-        KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n_pairs, passes, np, &sorted));
+// row r of a partition owns the keys whose high word is base + r
+__global__ void __launch_bounds__(kThreads) row_bounds_base_kernel(const uint64_t *__restrict__ keys, uint64_t count,
+                                                                   uint32_t base, uint32_t n_rows, uint64_t *__restrict__ start) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t cur = i < count ? (int64_t)(keys[i] >> 32) - (int64_t)base : (int64_t)n_rows;
+        int64_t prev = i > 0 ? (int64_t)(keys[i - 1] >> 32) - (int64_t)base : -1;
+        for (int64_t x = prev + 1; x <= cur; ++x) start[x] = i;
     }
-    uint32_t h_info[2] = {0, 0};
-    KG_TRY(read_back(ctx, info.p, h_info, 2));
-    if (h_info[1]) return ctx_fail(ctx, KOMBGPU_EINVAL, "edge endpoint >= n_vertices (%u)", n_vertices);
-    g->st.n_pairs = n_pairs;
-    return finish_graph(ctx, sorted, n_pairs, n_vertices, g);
 }
 
-int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
-                    uint32_t n_vertices, kombgpu_graph *g) {
+__global__ void __launch_bounds__(kThreads) part_cols_kernel(const uint64_t *__restrict__ keys, uint64_t count,
+                                                             uint32_t *__restrict__ col) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        col[i] = (uint32_t)keys[i];
+}
+
+__global__ void __launch_bounds__(kThreads) part_degree_kernel(const uint64_t *__restrict__ row_ptr, uint32_t n_rows,
+                                                               int32_t *__restrict__ deg, int32_t *__restrict__ max_deg) {
+    int32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (uint64_t)gridDim.x * blockDim.x) {
+        int32_t d = (int32_t)(row_ptr[i + 1] - row_ptr[i]);
+        deg[i] = d;
+        m = max(m, d);
+    }
+    m = warp_reduce_max(m);
+    if (lane_id() == 0 && m) atomicMax(max_deg, m);
+}
+
+struct AnyHeadFlag {  // unique of sorted directed entries (no loop test: routed entries never hold loops)
+    const uint64_t *keys;
+    __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+};
+
+// hits -> all clique pairs, sorted (duplicates still in).  pa / pb are the ping-pong buffers.
+int hits_to_sorted_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                         uint32_t n_vertices, DevBuf<uint64_t> &pa, DevBuf<uint64_t> &pb, uint64_t **psorted_out,
+                         uint64_t *n_pairs_out, kombgpu_stats *st) {
     if (n_hits >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_hits >= 2^32 is not supported on one device");
     const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
-    g->st.n_hits = n_hits;
+    st->n_hits = n_hits;
 
     // 1. (read, unitig) keys, sorted + unique  == per-read unitig SETS, mates merged
     DevBuf<uint64_t> ha, hb;
@@ -351,7 +315,7 @@ int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *
     uint32_t n_uniq = 0;
     KG_TRY(read_back(ctx, d_cnt.p, &n_uniq, 1));
     const uint64_t *hits = other;  // sorted unique hits, n_uniq of them
-    g->st.n_unique_hits = n_uniq;
+    st->n_unique_hits = n_uniq;
 
     // 2. reads with >= 2 unitigs -> segments; pairs per segment -> offsets
     DevBuf<uint32_t> seg_head, seg_tail;
@@ -368,12 +332,12 @@ int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *
     KG_TRY((device_scan<uint64_t>(ctx, n_seg, SegPairsIn{seg_head.p, seg_tail.p}, SegPairsOut{seg_base.p}, d_tot.p)));
     uint64_t n_pairs = 0;
     KG_TRY(read_back(ctx, d_tot.p, &n_pairs, 1));
-    g->st.n_pairs = n_pairs;
+    st->n_pairs = n_pairs;
+    *n_pairs_out = n_pairs;
     if (n_pairs >= (1ull << 32))
         return ctx_fail(ctx, KOMBGPU_EINVAL, "%llu clique pairs exceed the 2^32 per-device limit", (unsigned long long)n_pairs);
 
-    // 3. emit all pairs, sort, unique -> edges -> CSR
-    DevBuf<uint64_t> pa, pb;
+    // 3. emit all pairs, sort
     KG_ALLOC(ctx, pa, n_pairs);
     KG_ALLOC(ctx, pb, n_pairs);
     uint64_t *psorted = pa.p;
@@ -384,13 +348,194 @@ int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *
         KG_LAUNCH(ctx, emit_partition_kernel, grid_for(n_tiles, kThreads), kThreads, 0, seg_base.p, n_seg, n_tiles, tile_seg.p);
         KG_LAUNCH(ctx, emit_pairs_kernel, n_tiles, kThreads, 0, hits, seg_head.p, seg_base.p, n_seg, tile_seg.p, n_tiles,
                   n_pairs, pa.p);
-        // the hit buffers are no longer needed once the pairs exist
         int npp = plan_radix_passes(0, bn, 32, 32 + bn, passes);
         KG_TRY(radix_sort_u64(ctx, pa.p, pb.p, n_pairs, passes, npp, &psorted));
     }
-    ha.release();
-    hb.release();
-    return finish_graph(ctx, psorted, n_pairs, n_vertices, g);
+    *psorted_out = psorted;
+    return KOMBGPU_OK;
+}
+
+// (u, v) pairs -> canonical keys, sorted (duplicates and loops still in)
+int pairs_to_sorted_keys(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                         DevBuf<uint64_t> &ka, DevBuf<uint64_t> &kb, uint64_t **sorted_out) {
+    if (n_pairs >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_pairs >= 2^32 is not supported on one device");
+    const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
+    DevBuf<uint32_t> info(ctx, 2);
+    KG_ALLOC(ctx, ka, n_pairs);
+    KG_ALLOC(ctx, kb, n_pairs);
+    if (!info) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    uint64_t *sorted = ka.p;
+    if (n_pairs) {
+        KG_LAUNCH(ctx, pack_pairs_kernel, min(grid_for(n_pairs, kThreads), 148u * 16u), kThreads, 0, u, v, n_pairs, n_vertices,
+                  ka.p, info.p);
+        RadixPass passes[8];
+        int np = plan_radix_passes(0, bn, 32, 32 + bn, passes);
+        KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n_pairs, passes, np, &sorted));
+    }
+    uint32_t h_info[2] = {0, 0};
+    KG_TRY(read_back(ctx, info.p, h_info, 2));
+    if (h_info[1]) return ctx_fail(ctx, KOMBGPU_EINVAL, "edge endpoint >= n_vertices (%u)", n_vertices);
+    *sorted_out = sorted;
+    return KOMBGPU_OK;
+}
+
+}  // namespace
+
+// sorted pair keys (duplicates, loops possible) -> unique simple edges
+int unique_edges(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, DevBuf<uint64_t> &edges, uint64_t *n_edges) {
+    DevBuf<uint32_t> d_count(ctx, 1);
+    if (!d_count) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_ALLOC(ctx, edges, count);
+    KG_TRY((device_scan<uint32_t>(ctx, count, EdgeFlagIn{keys}, CompactKeysU64{keys, edges.p}, d_count.p)));
+    uint32_t n32 = 0;
+    KG_TRY(read_back(ctx, d_count.p, &n32, 1));
+    *n_edges = n32;
+    return KOMBGPU_OK;
+}
+
+// (v << 32 | u) copy of an edge list, stably sorted on v: the backward half of the adjacency in order
+int swapped_sorted(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t n_edges, uint32_t n_vertices, DevBuf<uint64_t> &a,
+                   DevBuf<uint64_t> &b, uint64_t **out) {
+    const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
+    KG_ALLOC(ctx, a, n_edges);
+    KG_ALLOC(ctx, b, n_edges);
+    *out = a.p;
+    if (n_edges) {
+        KG_LAUNCH(ctx, swap_pack_kernel, min(grid_for(n_edges, kThreads), 148u * 16u), kThreads, 0, edges, n_edges, a.p);
+        RadixPass passes[8];
+        int np = plan_radix_passes(32, 32 + bn, 0, 0, passes);
+        KG_TRY(radix_sort_u64(ctx, a.p, b.p, n_edges, passes, np, out));
+    }
+    return KOMBGPU_OK;
+}
+
+int lower_bounds_hi(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, const uint32_t *bounds_host, int nb,
+                    uint64_t *idx_host) {
+    DevBuf<uint32_t> d_b;
+    DevBuf<uint64_t> d_i;
+    KG_ALLOC(ctx, d_b, nb);
+    KG_ALLOC(ctx, d_i, nb);
+    KG_CUDA(ctx, cudaMemcpyAsync(d_b.p, bounds_host, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    KG_LAUNCH(ctx, lower_bounds_kernel, 1, 64, 0, keys, count, d_b.p, nb, d_i.p);
+    return read_back(ctx, d_i.p, idx_host, nb);
+}
+
+int hits_to_edges(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                  DevBuf<uint64_t> &edges, uint64_t *n_edges, kombgpu_stats *st) {
+    DevBuf<uint64_t> pa, pb;
+    uint64_t *psorted = nullptr, n_pairs = 0;
+    KG_TRY(hits_to_sorted_pairs(ctx, read_key, unitig, n_hits, n_vertices, pa, pb, &psorted, &n_pairs, st));
+    return unique_edges(ctx, psorted, n_pairs, edges, n_edges);
+}
+
+int pairs_to_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                   DevBuf<uint64_t> &edges, uint64_t *n_edges) {
+    DevBuf<uint64_t> ka, kb;
+    uint64_t *sorted = nullptr;
+    KG_TRY(pairs_to_sorted_keys(ctx, u, v, n_pairs, n_vertices, ka, kb, &sorted));
+    return unique_edges(ctx, sorted, n_pairs, edges, n_edges);
+}
+
+// unique simple edges (sorted, u < v) -> CSR of the symmetric graph
+int csr_from_edges(kombgpu_ctx *ctx, DevBuf<uint64_t> &edges, uint64_t E, uint32_t n, kombgpu_graph *g) {
+    g->n = n;
+    g->n_edges = E;
+    g->st.n_edges = E;
+    g->st.n_vertices = n;
+    DevBuf<uint64_t> sw_a, sw_b;
+    uint64_t *swapped = nullptr;
+    KG_TRY(swapped_sorted(ctx, edges.p, E, n, sw_a, sw_b, &swapped));
+    DevBuf<uint32_t> fwd_start, back_start;
+    KG_ALLOC(ctx, fwd_start, (size_t)n + 1);
+    KG_ALLOC(ctx, back_start, (size_t)n + 1);
+    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, edges.p, E, n, fwd_start.p);
+    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, swapped, E, n, back_start.p);
+
+    DevBuf<uint64_t> row_ptr;
+    DevBuf<int32_t> deg, max_deg(ctx, 1);
+    DevBuf<uint32_t> col;
+    KG_ALLOC(ctx, row_ptr, (size_t)n + 1);
+    KG_ALLOC(ctx, deg, n);
+    KG_ALLOC(ctx, col, 2 * E);
+    if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
+    KG_TRY((device_scan<uint64_t>(ctx, n, DegreeIn{fwd_start.p, back_start.p}, DegreeOut{row_ptr.p, deg.p},
+                                  (uint64_t *)nullptr)));
+    if (n) KG_LAUNCH(ctx, reduce_max_i32_kernel, min(grid_for(n, kThreads), 148u * 8u), kThreads, 0, deg.p, (uint64_t)n, max_deg.p);
+    KG_LAUNCH(ctx, set_u64_kernel, 1, 1, 0, row_ptr.p + n, 2 * E);
+    if (E)
+        KG_LAUNCH(ctx, fill_col_kernel, min(grid_for(E, kThreads), 148u * 16u), kThreads, 0, edges.p, swapped, E, row_ptr.p,
+                  fwd_start.p, back_start.p, col.p);
+    KG_TRY(read_back(ctx, max_deg.p, &g->st.max_degree, 1));
+    g->edges = edges.take();
+    g->row_ptr = row_ptr.take();
+    g->col = col.take();
+    g->deg = deg.take();
+    return KOMBGPU_OK;
+}
+
+// directed entries (src << 32 | dst) with src in [v_lo, v_lo + n_local), any order, duplicates allowed
+// -> CSR rows of this rank: row_ptr[n_local + 1], col[] = global ids (every row ascending), deg[]
+int csr_from_directed(kombgpu_ctx *ctx, const uint64_t *entries, uint64_t count, uint32_t v_lo, uint32_t n_local,
+                      uint32_t n_global, uint64_t **row_ptr_out, uint32_t **col_out, int32_t **deg_out, int32_t *max_deg_out,
+                      uint64_t *n_directed_out) {
+    if (count >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "more than 2^32 directed entries on one device");
+    const int bn = bits_for(n_global > 0 ? n_global - 1 : 0);
+    DevBuf<uint64_t> ka, kb, uniq;
+    KG_ALLOC(ctx, ka, count);
+    KG_ALLOC(ctx, kb, count);
+    uint64_t *sorted = ka.p;
+    if (count) {
+        KG_CUDA(ctx, cudaMemcpyAsync(ka.p, entries, count * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        RadixPass passes[8];
+        int np = plan_radix_passes(0, bn, 32, 32 + bn, passes);
+        KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, count, passes, np, &sorted));
+    }
+    DevBuf<uint32_t> d_count(ctx, 1);
+    if (!d_count) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_ALLOC(ctx, uniq, count);
+    KG_TRY((device_scan<uint32_t>(ctx, count, AnyHeadFlag{sorted}, CompactKeysU64{sorted, uniq.p}, d_count.p)));
+    uint32_t nd32 = 0;
+    KG_TRY(read_back(ctx, d_count.p, &nd32, 1));
+    const uint64_t nd = nd32;
+    DevBuf<uint64_t> row_ptr;
+    DevBuf<uint32_t> col;
+    DevBuf<int32_t> deg, max_deg(ctx, 1);
+    KG_ALLOC(ctx, row_ptr, (size_t)n_local + 1);
+    KG_ALLOC(ctx, col, nd);
+    KG_ALLOC(ctx, deg, n_local);
+    if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
+    KG_LAUNCH(ctx, row_bounds_base_kernel, min(grid_for(nd + 1, kThreads), 148u * 16u), kThreads, 0, uniq.p, nd, v_lo, n_local,
+              row_ptr.p);
+    if (nd) KG_LAUNCH(ctx, part_cols_kernel, min(grid_for(nd, kThreads), 148u * 16u), kThreads, 0, uniq.p, nd, col.p);
+    if (n_local)
+        KG_LAUNCH(ctx, part_degree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, row_ptr.p, n_local, deg.p,
+                  max_deg.p);
+    KG_TRY(read_back(ctx, max_deg.p, max_deg_out, 1));
+    *n_directed_out = nd;
+    *row_ptr_out = row_ptr.take();
+    *col_out = col.take();
+    *deg_out = deg.take();
+    return KOMBGPU_OK;
+}
+
+int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                     kombgpu_graph *g) {
+    DevBuf<uint64_t> edges;
+    uint64_t E = 0;
+    g->st.n_pairs = n_pairs;
+    KG_TRY(pairs_to_edges(ctx, u, v, n_pairs, n_vertices, edges, &E));
+    return csr_from_edges(ctx, edges, E, n_vertices, g);
+}
+
+int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                    uint32_t n_vertices, kombgpu_graph *g) {
+    DevBuf<uint64_t> edges;
+    uint64_t E = 0;
+    KG_TRY(hits_to_edges(ctx, read_key, unitig, n_hits, n_vertices, edges, &E, &g->st));
+    return csr_from_edges(ctx, edges, E, n_vertices, g);
 }
 
 void graph_release(kombgpu_graph *g) {

@@ -27,6 +27,19 @@ int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *
 int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
                      kombgpu_graph *g);
 
+// building blocks of stage 1 shared with the partitioned (multi-GPU) path (build.cu)
+int hits_to_edges(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                  DevBuf<uint64_t> &edges, uint64_t *n_edges, kombgpu_stats *st);
+int pairs_to_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
+                   DevBuf<uint64_t> &edges, uint64_t *n_edges);
+int swapped_sorted(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t n_edges, uint32_t n_vertices, DevBuf<uint64_t> &a,
+                   DevBuf<uint64_t> &b, uint64_t **out);
+int lower_bounds_hi(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, const uint32_t *bounds_host, int nb,
+                    uint64_t *idx_host);
+int csr_from_directed(kombgpu_ctx *ctx, const uint64_t *entries, uint64_t count, uint32_t v_lo, uint32_t n_local,
+                      uint32_t n_global, uint64_t **row_ptr_out, uint32_t **col_out, int32_t **deg_out, int32_t *max_deg_out,
+                      uint64_t *n_directed_out);
+
 // stage 2 (peel.cu)
 int peel_coreness(kombgpu_graph *g);
 
