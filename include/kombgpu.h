@@ -78,13 +78,19 @@ int kombgpu_ctx_create(int device, kombgpu_ctx **out);
 void kombgpu_ctx_destroy(kombgpu_ctx *ctx);
 
 /* Run all work of this context on an existing CUDA stream (a cudaStream_t cast
- * to void*, e.g. torch.cuda.current_stream().cuda_stream).  NULL restores the
- * context's own stream. */
+ * to void*, e.g. torch.cuda.current_stream().cuda_stream).  As everywhere in
+ * CUDA, NULL is the legacy default stream (which is what torch uses unless told
+ * otherwise).  kombgpu_ctx_reset_stream returns to the context's private
+ * non-blocking stream (the state after kombgpu_ctx_create). */
 int kombgpu_ctx_set_stream(kombgpu_ctx *ctx, void *cuda_stream);
+int kombgpu_ctx_reset_stream(kombgpu_ctx *ctx);
 
 /* Text of the last error on this context (never NULL).  With ctx == NULL:
  * the last error of a failed kombgpu_ctx_create on this thread. */
 const char *kombgpu_last_error(const kombgpu_ctx *ctx);
+
+/* Number of this library's kernels launched through the context so far. */
+int kombgpu_ctx_launches(const kombgpu_ctx *ctx, uint64_t *launches);
 
 /* Release cached device workspace held by the context. */
 int kombgpu_ctx_trim(kombgpu_ctx *ctx);

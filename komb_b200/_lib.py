@@ -38,8 +38,10 @@ SIGNATURES = {
     "kombgpu_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
     "kombgpu_ctx_destroy": (None, [c_void_p]),
     "kombgpu_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
+    "kombgpu_ctx_reset_stream": (c_int, [c_void_p]),
     "kombgpu_last_error": (c_char_p, [c_void_p]),
     "kombgpu_ctx_trim": (c_int, [c_void_p]),
+    "kombgpu_ctx_launches": (c_int, [c_void_p, POINTER(c_uint64)]),
     "kombgpu_build_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_build_graph_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_graph_from_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),

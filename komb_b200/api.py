@@ -62,7 +62,18 @@ class Context:
             raise KombGpuError(rc, self._lib.kombgpu_last_error(self._h).decode())
 
     def set_stream(self, cuda_stream: int | None):
+        """Run on an existing CUDA stream handle; 0 / None is CUDA's legacy default stream
+        (torch's default).  reset_stream() goes back to the context's private stream."""
         self._check(self._lib.kombgpu_ctx_set_stream(self._h, c_void_p(cuda_stream or 0)))
+
+    def reset_stream(self):
+        self._check(self._lib.kombgpu_ctx_reset_stream(self._h))
+
+    def launches(self) -> int:
+        """Kernels of libkombgpu launched through this context so far."""
+        n = c_uint64()
+        self._check(self._lib.kombgpu_ctx_launches(self._h, byref(n)))
+        return n.value
 
     def trim(self):
         self._check(self._lib.kombgpu_ctx_trim(self._h))

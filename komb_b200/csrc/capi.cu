@@ -223,11 +223,24 @@ void kombgpu_ctx_destroy(kombgpu_ctx *ctx) {
 int kombgpu_ctx_set_stream(kombgpu_ctx *ctx, void *cuda_stream) {
     if (!ctx) return KOMBGPU_EINVAL;
     KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL = the legacy default stream
+    return KOMBGPU_OK;
+}
+
+int kombgpu_ctx_reset_stream(kombgpu_ctx *ctx) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return KOMBGPU_OK;
 }
 
 const char *kombgpu_last_error(const kombgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int kombgpu_ctx_launches(const kombgpu_ctx *ctx, uint64_t *launches) {
+    if (!ctx || !launches) return KOMBGPU_EINVAL;
+    *launches = ctx->launches;
+    return KOMBGPU_OK;
+}
 
 int kombgpu_ctx_trim(kombgpu_ctx *ctx) {
     if (!ctx) return KOMBGPU_EINVAL;

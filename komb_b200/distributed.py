@@ -142,6 +142,8 @@ class CudaEngine:
         self.ctx = ctx
         self.lib = ctx._lib
         self.device = torch.device("cuda", ctx.device)
+        # the exchanges are torch collectives ordered on torch's current stream: the kernels must run there too
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _check(self, rc):
         self.ctx._check(rc)

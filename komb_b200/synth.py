@@ -43,8 +43,17 @@ def _powerlaw_unitigs(rng: np.random.Generator, count: int, n: int, alpha: float
     return u.astype(np.uint32)
 
 
+def scramble_ids(u: np.ndarray, n: int) -> np.ndarray:
+    """Fixed bijection on [0, n): u -> (u * A + B) mod n with gcd(A, n) = 1.  Real unitig ids carry no
+    degree order; the power-law generator's do (low id = hub), which would unbalance a range partition."""
+    a = 2654435761
+    while np.gcd(a, n) != 1:
+        a += 2
+    return ((u.astype(np.uint64) * np.uint64(a) + np.uint64(12345)) % np.uint64(n)).astype(np.uint32)
+
+
 def metagenome_hits(n_unitigs: int, n_read_pairs: int, seed: int = 11, alpha: float = 0.5,
-                    read_offset: int = 0, local_window: int = 0) -> tuple[HitSet, HitSet]:
+                    read_offset: int = 0, local_window: int = 0, scramble: bool = False) -> tuple[HitSet, HitSet]:
     """cfg2-style hit sets for the two mate files.
 
     Read pair r has k1 hits in mate file 1 and k2 in mate file 2, k uniform over
@@ -67,6 +76,8 @@ def metagenome_hits(n_unitigs: int, n_read_pairs: int, seed: int = 11, alpha: fl
             unitig = ((centre[reads] + off) % n_unitigs).astype(np.uint32)
         else:
             unitig = _powerlaw_unitigs(rng, h, n_unitigs, alpha)
+        if scramble:
+            unitig = scramble_ids(unitig, n_unitigs)
         mates.append(HitSet((reads + read_offset).astype(np.uint32), unitig))
     return mates[0], mates[1]
 
