@@ -189,6 +189,8 @@ def run_ours(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         return run_ours_multi(args, rank, world, local_rank)
 
@@ -359,14 +361,14 @@ def run_ours_multi(args, rank, world, local_rank):
 
     stage_t = {}
 
-    def step_device():
+    def step_device(mode="auto"):
         marks = [time.perf_counter()]
 
         def tick(name):
             torch.cuda.synchronize()
             marks.append(time.perf_counter())
             stage_t[name] = stage_t.get(name, 0.0) + (marks[-1] - marks[-2])
-        return analyse_partitioned(eng, comm, n_global, read_key=rk_d, unitig=ut_d, timer=tick)
+        return analyse_partitioned(eng, comm, n_global, read_key=rk_d, unitig=ut_d, timer=tick, peel_mode=mode)
 
     def step_e2e():
         a = rk_h.cuda(non_blocking=True)
@@ -402,14 +404,30 @@ def run_ours_multi(args, rank, world, local_rank):
         e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))
 
+    # the partitioned peel (exchange per sub-round) timed once as a secondary number
+    saved = dict(stage_t)
+    stage_t.clear()
+    res_p, t_part = timed(lambda: step_device("partitioned"))
+    part_t = dict(stage_t)
+    stage_t.clear()
+    stage_t.update(saved)
+
     tot = comm.all_gather_ints([rk_h.numel(), d2h])
     H = int(tot[:, 0].sum())
     E, n = res.n_edges, n_global
     P = res.stats["sum_pairs"]
     b_peel = 24 * E + 16 * n
-    peel_s = stage_t.get("peel", 0.0) / max(args.steps, 1)
-    build_s = stage_t.get("build", 0.0) / max(args.steps, 1)
-    corea_s = stage_t.get("corea", 0.0) / max(args.steps, 1)
+    steps = max(args.steps, 1)
+    build_s = stage_t.get("build", 0.0) / steps
+    gather_s = stage_t.get("gather", 0.0) / steps
+    if res.stats["peel_mode"] == "gather":
+        peel_s = res.stats["ms_peel"] * 1e-3
+        corea_s = res.stats["ms_corea"] * 1e-3
+        peel_kernel_s = res.stats["ms_peel_kernel"] * 1e-3
+    else:
+        peel_s = stage_t.get("peel", 0.0) / steps
+        corea_s = stage_t.get("corea", 0.0) / steps
+        peel_kernel_s = peel_s
     if rank == 0:
         line = {
             "metric": METRIC, "value": H / (ms_per_step * 1e-3), "unit": "hits/s", "n_gpus": world, "steps": args.steps,
@@ -418,19 +436,28 @@ def run_ours_multi(args, rank, world, local_rank):
             "config": {"workload": f"cfg2 x{world}: synthetic metagenome unitig graph, 1M unitigs + 5M read pairs (~20M hits) per GPU, "
                                    "unitig ids scrambled by a fixed bijection, graph partitioned by unitig-id range", "n_unitigs": n, "n_read_pairs": N_READ_PAIRS * world,
                        "n_hits": H, "n_pairs": P, "n_edges": E, "max_coreness": res.max_coreness, "peel_levels": res.stats["levels"],
-                       "exchange_subrounds": res.stats["exchange_subrounds"], "seed": SEED, "corea_key": "ref32",
-                       "parallelism": f"unitig-range x{world}, NCCL all_to_all per peel sub-round",
+                       "seed": SEED, "corea_key": "ref32", "peel_mode": res.stats["peel_mode"],
+                       "parallelism": f"unitig-range partition x{world}: build distributed (NCCL all_to_all of edge entries); "
+                                      + ("CSR all-gathered over NVLink, persistent peel + CORE-A on every GPU"
+                                         if res.stats["peel_mode"] == "gather" else "peel partitioned, NCCL all_to_all per sub-round"),
                        "l2": "256 MB flush between timed steps; inputs exceed L2"},
             "stages": {"build": {"ms": build_s * 1e3, "hits_per_s": H / build_s if build_s else None},
+                       "gather_csr": {"ms": gather_s * 1e3},
                        "peel": {"ms": peel_s * 1e3, "edges_per_s": E / peel_s if peel_s else None, "algorithmic_bytes": b_peel,
                                 "frac_hbm": (b_peel / peel_s / 1e9 / (hbm_gbs * world)) if peel_s else None},
-                       "corea": {"ms": corea_s * 1e3, "vertices_per_s": n / corea_s if corea_s else None}},
+                       "corea": {"ms": corea_s * 1e3, "vertices_per_s": n / corea_s if corea_s else None},
+                       "peel_partitioned": {"ms_per_step": t_part, "peel_ms": part_t.get("peel", 0.0) * 1e3,
+                                            "exchange_subrounds": res_p.stats["exchange_subrounds"],
+                                            "hits_per_s": H / (t_part * 1e-3)}},
             "peel_edges_per_s": E / peel_s if peel_s else None,
             "build_hits_per_s": H / build_s if build_s else None,
-            "roofline": {"kernel": "distributed peel (part_process_kernel + exchange, all sub-rounds)", "bound": "hbm",
-                         "achieved": b_peel / peel_s / 1e9 if peel_s else None, "peak": hbm_gbs * world, "unit": "GB/s",
-                         "frac": (b_peel / peel_s / 1e9 / (hbm_gbs * world)) if peel_s else None, "traffic": None,
-                         "algorithmic_bytes": b_peel, "peak_source": peak_src + f" x {world} GPUs"},
+            "roofline": {"kernel": "peel_kernel (persistent cooperative frontier peel; whole graph on every GPU)"
+                                   if res.stats["peel_mode"] == "gather" else "part_process_kernel + exchange, all sub-rounds",
+                         "bound": "hbm", "achieved": b_peel / peel_kernel_s / 1e9 if peel_kernel_s else None,
+                         "peak": hbm_gbs * world, "unit": "GB/s",
+                         "frac": (b_peel / peel_kernel_s / 1e9 / (hbm_gbs * world)) if peel_kernel_s else None, "traffic": None,
+                         "algorithmic_bytes": b_peel, "kernel_ms": peel_kernel_s * 1e3,
+                         "peak_source": peak_src + f" x {world} GPUs (aggregate)"},
             "e2e": {"value": H / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": 8 * H, "d2h_bytes_per_step": int(tot[:, 1].sum()),
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches.sum()),

@@ -115,6 +115,13 @@ int kombgpu_graph_from_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t
 int kombgpu_graph_from_edges_dev(kombgpu_ctx *ctx, const uint32_t *u_dev, const uint32_t *v_dev,
                                  uint64_t n_pairs, uint32_t n_vertices, kombgpu_graph **out);
 
+/* Adopt an existing CSR of a simple symmetric graph (device pointers; row_ptr[n+1],
+ * col[row_ptr[n]], rows need not be sorted).  The arrays are copied.  Used by the
+ * multi-GPU path after all-gathering the rank-local rows; the canonical edge
+ * list is not materialised (kombgpu_graph_edges returns KOMBGPU_ESTATE). */
+int kombgpu_graph_from_csr_dev(kombgpu_ctx *ctx, const uint64_t *row_ptr_dev, const uint32_t *col_dev,
+                               uint32_t n_vertices, kombgpu_graph **out);
+
 void kombgpu_graph_destroy(kombgpu_graph *g);
 
 /* |V| and |E| of the simple graph (igraph_vcount / igraph_ecount,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "kombgpu_build_graph_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_graph_from_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_graph_from_edges_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_graph_from_csr_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, POINTER(c_void_p)]),
     "kombgpu_graph_destroy": (None, [c_void_p]),
     "kombgpu_graph_counts": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64)]),
     "kombgpu_graph_edges": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -104,6 +104,13 @@ class Context:
         return self._pair_call(self._lib.kombgpu_graph_from_edges, self._lib.kombgpu_graph_from_edges_dev,
                                u, v, int(n_vertices))
 
+    def graph_from_csr(self, row_ptr, col, n_vertices: int) -> "Graph":
+        """Adopt a device-resident CSR (torch CUDA tensors: int64 row_ptr[n+1], int32 col)."""
+        g = c_void_p()
+        self._check(self._lib.kombgpu_graph_from_csr_dev(self._h, c_void_p(row_ptr.data_ptr()),
+                                                         c_void_p(col.data_ptr() if col.numel() else 0), int(n_vertices), byref(g)))
+        return Graph(self, g, (row_ptr, col))
+
     def corea(self, coreness, degree, key_mode: int = KEY_REF32) -> np.ndarray:
         """CoreA::getAnomalyScore on host arrays."""
         c, d = _host(coreness, np.int32), _host(degree, np.int32)

@@ -521,6 +521,33 @@ int csr_from_directed(kombgpu_ctx *ctx, const uint64_t *entries, uint64_t count,
     return KOMBGPU_OK;
 }
 
+// copy an existing CSR (device) into a graph; degrees from the row lengths
+int adopt_csr(kombgpu_ctx *ctx, const uint64_t *row_ptr, const uint32_t *col, uint32_t n, kombgpu_graph *g) {
+    uint64_t n_dir = 0;
+    KG_TRY(read_back(ctx, row_ptr + n, &n_dir, 1));
+    if (n_dir && !col) return ctx_fail(ctx, KOMBGPU_EINVAL, "null col array");
+    DevBuf<uint64_t> rp;
+    DevBuf<uint32_t> cl;
+    DevBuf<int32_t> deg, max_deg(ctx, 1);
+    KG_ALLOC(ctx, rp, (size_t)n + 1);
+    KG_ALLOC(ctx, cl, n_dir);
+    KG_ALLOC(ctx, deg, n);
+    if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemcpyAsync(rp.p, row_ptr, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n_dir) KG_CUDA(ctx, cudaMemcpyAsync(cl.p, col, n_dir * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
+    if (n) KG_LAUNCH(ctx, part_degree_kernel, min(grid_for(n, kThreads), 148u * 8u), kThreads, 0, rp.p, n, deg.p, max_deg.p);
+    KG_TRY(read_back(ctx, max_deg.p, &g->st.max_degree, 1));
+    g->n = n;
+    g->n_edges = n_dir / 2;
+    g->st.n_vertices = n;
+    g->st.n_edges = n_dir / 2;
+    g->row_ptr = rp.take();
+    g->col = cl.take();
+    g->deg = deg.take();
+    return KOMBGPU_OK;
+}
+
 int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
                      kombgpu_graph *g) {
     DevBuf<uint64_t> edges;

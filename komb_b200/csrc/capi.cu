@@ -265,6 +265,23 @@ int kombgpu_graph_from_edges_dev(kombgpu_ctx *ctx, const uint32_t *u, const uint
     return build_common(ctx, u, v, n_pairs, n_vertices, false, build_from_pairs, out);
 }
 
+int kombgpu_graph_from_csr_dev(kombgpu_ctx *ctx, const uint64_t *row_ptr, const uint32_t *col, uint32_t n, kombgpu_graph **out) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if (!out || !row_ptr || n >= 0xfffffffeu) return ctx_fail(ctx, KOMBGPU_EINVAL, "bad argument");
+    *out = nullptr;
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    kombgpu_graph *g = new (std::nothrow) kombgpu_graph();
+    if (!g) return ctx_fail(ctx, KOMBGPU_ENOMEM, "host allocation");
+    g->ctx = ctx;
+    g->st.max_coreness = -1;
+    const uint64_t launches0 = ctx->launches;
+    int rc = adopt_csr(ctx, row_ptr, col, n, g);
+    g->st.kernel_launches = ctx->launches - launches0;
+    if (rc != KOMBGPU_OK) { graph_release(g); delete g; return rc; }
+    *out = g;
+    return KOMBGPU_OK;
+}
+
 void kombgpu_graph_destroy(kombgpu_graph *g) {
     if (!g) return;
     graph_release(g);
@@ -283,6 +300,7 @@ int kombgpu_graph_edges(const kombgpu_graph *g, uint32_t *u, uint32_t *v) {
     kombgpu_ctx *ctx = g->ctx;
     if (!u || !v) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
     if (g->n_edges == 0) return KOMBGPU_OK;
+    if (!g->edges) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no canonical edge list");
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf<uint32_t> du, dv;
     KG_ALLOC(ctx, du, g->n_edges);

@@ -224,6 +224,41 @@ class CudaEngine:
         core = self.torch.as_tensor(_DevArray(ptrs[3].value, n, "<i4", part), device=self.device).clone()
         return deg, core
 
+    def part_csr(self, part):
+        """(row lengths int32[n_local], col int32[n_directed]) of the local rows: zero-copy views."""
+        c = self.part_counts(part)
+        ptrs = [c_void_p() for _ in range(4)]
+        self._check(self.lib.kombgpu_part_device_arrays(part, *[byref(p) for p in ptrs]))
+        z = self.torch.zeros(0, dtype=self.torch.int32, device=self.device)
+        deg = self.torch.as_tensor(_DevArray(ptrs[2].value, c["n_local"], "<i4", part), device=self.device) if c["n_local"] else z
+        col = self.torch.as_tensor(_DevArray(ptrs[1].value, c["n_directed"], "<i4", part), device=self.device) if c["n_directed"] else z
+        return deg, col
+
+    def gather_peel(self, deg_full, col_full, n: int, key_mode: int):
+        """Whole graph on this rank (all-gathered rows): persistent single-GPU peel + CORE-A.
+        Returns (degree, coreness, score) as torch tensors plus (max_score, max_coreness, stats)."""
+        torch = self.torch
+        row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        if n:
+            torch.cumsum(deg_full.to(torch.int64), 0, out=row_ptr[1:])
+        g = self.ctx.graph_from_csr(row_ptr, col_full, n)
+        try:
+            g.analyse(key_mode)
+            arr = g.device_arrays()
+            st = g.stats()
+            mc, ms = g.summary()
+            if n == 0:
+                zi = torch.zeros(0, dtype=torch.int32, device=self.device)
+                return zi, zi.clone(), torch.zeros(0, dtype=torch.float64, device=self.device), 0.0, 0, st
+            core = torch.as_tensor(_DevArray(arr["coreness"], n, "<i4", g), device=self.device).clone()
+            score = torch.as_tensor(_DevArray(arr["score"], n, "<f8", g), device=self.device).clone()
+            return deg_full, core, score, ms, mc, st
+        finally:
+            g.close()
+
+    def device_memory_bytes(self) -> int:
+        return int(self.torch.cuda.get_device_properties(self.device).total_memory)
+
     def corea(self, core, deg, key_mode: int):
         n = core.numel()
         score = self.torch.empty(n, dtype=self.torch.float64, device=self.device)
@@ -257,10 +292,19 @@ class DistResult:
 
 
 def analyse_partitioned(engine, comm: Comm, n_global: int, *, read_key=None, unitig=None, pairs=None,
-                        key_mode: int = KEY_REF32, timer=None) -> DistResult:
+                        key_mode: int = KEY_REF32, timer=None, peel_mode: str = "auto") -> DistResult:
     """Run build -> k-core -> CORE-A over all ranks.  Every rank passes the hits of
     ITS reads (`read_key`, `unitig`: both mates, global unitig ids) or its share of
-    an edge list (`pairs=(u, v)`)."""
+    an edge list (`pairs=(u, v)`).
+
+    peel_mode
+      "partitioned"  the peel runs on the range partition, remote decrements exchanged per
+                     sub-round (works for graphs larger than one device's HBM);
+      "gather"       the rank-local CSR rows are all-gathered (NVLink) and every rank runs the
+                     persistent single-GPU peel on the whole graph.  The peel is bound by its
+                     dependency depth, not by bytes, so splitting it over ranks only adds an
+                     exchange latency to every one of its sub-rounds; the build stays distributed;
+      "auto"         "gather" when the whole CSR takes under a quarter of one device's memory."""
     r, world = comm.rank, comm.world
     bounds = partition_bounds(n_global, world)
     tick = timer or (lambda name: None)
@@ -273,6 +317,31 @@ def analyse_partitioned(engine, comm: Comm, n_global: int, *, read_key=None, uni
     part = engine.build_part(recv, bounds[r], bounds[r + 1], n_global)
     pc = engine.part_counts(part)
     tick("build")
+
+    tot = comm.all_gather_ints([pc["n_directed"], es_counts["n_edges"], es_counts["n_pairs"]])
+    n_directed_global = int(tot[:, 0].sum())
+    base_stats = {"local_edges": es_counts["n_edges"], "local_pairs": es_counts["n_pairs"],
+                  "n_directed_local": pc["n_directed"], "sum_local_edges": int(tot[:, 1].sum()),
+                  "sum_pairs": int(tot[:, 2].sum())}
+    if peel_mode == "auto":
+        csr_bytes = 4 * n_directed_global + 24 * n_global
+        peel_mode = "gather" if world > 1 and 4 * csr_bytes < engine.device_memory_bytes() else "partitioned"
+
+    if peel_mode == "gather":
+        # ---- stage 2+3 on the gathered graph ------------------------------------
+        deg_loc, col_loc = engine.part_csr(part)
+        deg_full = comm.all_gather_var(deg_loc)
+        col_full = comm.all_gather_var(col_loc)
+        engine.destroy_part(part)
+        tick("gather")
+        deg_f, core_f, score_f, max_score, max_core, gst = engine.gather_peel(deg_full, col_full, n_global, key_mode)
+        tick("peel+corea")
+        lo, hi = bounds[r], bounds[r + 1]
+        return DistResult(lo, hi, deg_f[lo:hi], core_f[lo:hi], score_f[lo:hi], float(max_score), int(max_core),
+                          n_directed_global // 2,
+                          dict(base_stats, peel_mode="gather", levels=int(gst.get("peel_levels", 0)), exchange_subrounds=0,
+                               decrements_received=0, ms_peel=float(gst.get("ms_peel", 0.0)), ms_corea=float(gst.get("ms_corea", 0.0)),
+                               ms_peel_kernel=float(gst.get("ms_peel_kernel", 0.0))))
 
     # ---- stage 2: peel --------------------------------------------------------
     engine.peel_begin(part)
@@ -310,10 +379,7 @@ def analyse_partitioned(engine, comm: Comm, n_global: int, *, read_key=None, uni
     score = score_full[bounds[r]:bounds[r + 1]]
     tick("corea")
 
-    tot = comm.all_gather_ints([pc["n_directed"], es_counts["n_edges"], es_counts["n_pairs"]])
     engine.destroy_part(part)
-    return DistResult(bounds[r], bounds[r + 1], deg, core, score, float(max_score), max_core, int(tot[:, 0].sum()) // 2,
-                      {"levels": levels, "exchange_subrounds": subrounds, "decrements_received": exchanged,
-                       "local_edges": es_counts["n_edges"], "local_pairs": es_counts["n_pairs"],
-                       "n_directed_local": pc["n_directed"], "sum_local_edges": int(tot[:, 1].sum()),
-                       "sum_pairs": int(tot[:, 2].sum())})
+    return DistResult(bounds[r], bounds[r + 1], deg, core, score, float(max_score), max_core, n_directed_global // 2,
+                      dict(base_stats, peel_mode="partitioned", levels=levels, exchange_subrounds=subrounds,
+                           decrements_received=exchanged))

@@ -102,5 +102,22 @@ class NumpyEngine:
         s = oracle.corea(np.asarray(core), np.asarray(deg), key_mode)
         return s, float(s.max()) if s.size else 0.0
 
+    def part_csr(self, p):
+        return p.deg.copy(), p.col.astype(np.int32)
+
+    def device_memory_bytes(self):
+        return 1 << 34
+
+    def gather_peel(self, deg_full, col_full, n, key_mode):
+        deg_full = np.asarray(deg_full).astype(np.int64)
+        col = np.asarray(col_full).astype(np.int64)
+        src = np.repeat(np.arange(n, dtype=np.int64), deg_full)
+        keep = src < col
+        edges = np.sort(oracle.pack_edges(src[keep].astype(np.uint32), col[keep].astype(np.uint32)))
+        deg, core = oracle.coreness(n, edges)
+        assert np.array_equal(deg, deg_full)
+        score = oracle.corea(core, deg, key_mode)
+        return deg, core, score, float(score.max()) if n else 0.0, int(core.max()) if n else 0, {"peel_levels": len(set(core.tolist()))}
+
     def destroy_part(self, p):
         pass

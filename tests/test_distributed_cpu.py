@@ -23,7 +23,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir, case):
+def _worker(rank, world, port, out_dir, case, peel_mode="partitioned"):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
     import torch.distributed as dist
@@ -44,11 +44,11 @@ def _worker(rank, world, port, out_dir, case):
         sel2 = (m2.read_key >= lo) & (m2.read_key < hi)
         rk = np.concatenate([m1.read_key[sel1], m2.read_key[sel2]])
         ut = np.concatenate([m1.unitig[sel1], m2.unitig[sel2]])
-        res = analyse_partitioned(NumpyEngine(), comm, n, read_key=rk, unitig=ut)
+        res = analyse_partitioned(NumpyEngine(), comm, n, read_key=rk, unitig=ut, peel_mode=peel_mode)
     else:
         u, v = synth.rmat_edges(11, reads, n_vertices=n, seed=seed)
         sl = slice(len(u) * rank // world, len(u) * (rank + 1) // world)
-        res = analyse_partitioned(NumpyEngine(), comm, n, pairs=(u[sl], v[sl]), key_mode=1)
+        res = analyse_partitioned(NumpyEngine(), comm, n, pairs=(u[sl], v[sl]), key_mode=1, peel_mode=peel_mode)
     with open(Path(out_dir) / f"rank{rank}.pkl", "wb") as f:
         pickle.dump({"v_lo": res.v_lo, "v_hi": res.v_hi, "deg": np.asarray(res.degree), "core": np.asarray(res.coreness),
                      "score": np.asarray(res.score), "max_score": res.max_score, "max_core": res.max_coreness,
@@ -57,11 +57,13 @@ def _worker(rank, world, port, out_dir, case):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case", [(2, (1500, 4000, 3, "hits")), (3, (1000, 3000, 4, "hits")), (2, (1200, 9000, 5, "pairs"))])
-def test_partitioned_path_matches_single_process(tmp_path, oracle_mod, world, case):
+@pytest.mark.parametrize("world,case,peel_mode", [(2, (1500, 4000, 3, "hits"), "partitioned"), (3, (1000, 3000, 4, "hits"), "partitioned"),
+                                                  (2, (1200, 9000, 5, "pairs"), "partitioned"), (2, (1500, 4000, 3, "hits"), "auto"),
+                                                  (3, (1200, 9000, 5, "pairs"), "gather")])
+def test_partitioned_path_matches_single_process(tmp_path, oracle_mod, world, case, peel_mode):
     from komb_b200 import synth
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path), case), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), case, peel_mode), nprocs=world, join=True)
     parts = [pickle.load(open(tmp_path / f"rank{r}.pkl", "rb")) for r in range(world)]
     n, reads, seed, kind = case
     if kind == "hits":
@@ -81,7 +83,10 @@ def test_partitioned_path_matches_single_process(tmp_path, oracle_mod, world, ca
     for p in parts:
         assert p["n_edges"] == edges.shape[0] and p["max_core"] == core.max()
         assert abs(p["max_score"] - score.max()) < 1e-12
-    assert parts[0]["stats"]["exchange_subrounds"] > 0          # the peel really crossed partitions
+    if peel_mode == "partitioned":
+        assert parts[0]["stats"]["exchange_subrounds"] > 0      # the peel really crossed partitions
+    else:
+        assert parts[0]["stats"]["peel_mode"] == "gather"
 
 
 def test_single_rank_needs_no_process_group(oracle_mod):
@@ -90,7 +95,7 @@ def test_single_rank_needs_no_process_group(oracle_mod):
     from komb_b200 import synth
     from komb_b200.distributed import Comm, analyse_partitioned
     u, v = synth.rmat_edges(9, 3000, n_vertices=400, seed=1)
-    res = analyse_partitioned(NumpyEngine(), Comm(), 400, pairs=(u, v))
+    res = analyse_partitioned(NumpyEngine(), Comm(), 400, pairs=(u, v), peel_mode="partitioned")
     deg, core = oracle_mod.coreness(400, oracle_mod.simplify(u, v))
     assert np.array_equal(res.coreness, core) and np.array_equal(res.degree, deg)
     assert res.stats["exchange_subrounds"] == 0

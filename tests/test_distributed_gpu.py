@@ -43,7 +43,7 @@ def _expected(oracle, case):
     return edges, deg, core, oracle.corea(core, deg, oracle.KEY_REF32)
 
 
-def _run_rank(rank, world, case):
+def _run_rank(rank, world, case, peel_mode="partitioned"):
     import torch
     import komb_b200
     from komb_b200.distributed import Comm, CudaEngine, analyse_partitioned
@@ -56,22 +56,22 @@ def _run_rank(rank, world, case):
     torch.cuda.synchronize()
     eng = CudaEngine(ctx)
     if case[3] == "hits":
-        res = analyse_partitioned(eng, Comm(), case[0], read_key=ta, unitig=tb)
+        res = analyse_partitioned(eng, Comm(), case[0], read_key=ta, unitig=tb, peel_mode=peel_mode)
     else:
-        res = analyse_partitioned(eng, Comm(), case[0], pairs=(ta, tb))
+        res = analyse_partitioned(eng, Comm(), case[0], pairs=(ta, tb), peel_mode=peel_mode)
     out = {"v_lo": res.v_lo, "v_hi": res.v_hi, "deg": res.degree.cpu().numpy(), "core": res.coreness.cpu().numpy(),
            "score": res.score.cpu().numpy(), "max_core": res.max_coreness, "n_edges": res.n_edges, "stats": res.stats}
     ctx.close()
     return out
 
 
-def _worker(rank, world, port, out_dir, case):
+def _worker(rank, world, port, out_dir, case, peel_mode):
     sys.path.insert(0, str(ROOT))
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    out = _run_rank(rank, world, case)
+    out = _run_rank(rank, world, case, peel_mode)
     with open(Path(out_dir) / f"rank{rank}.pkl", "wb") as f:
         pickle.dump(out, f)
     dist.barrier()
@@ -92,10 +92,14 @@ def test_partition_kernels_world1(oracle_mod, case):
     _check([_run_rank(0, 1, case)], _expected(oracle_mod, case))
 
 
-@pytest.mark.parametrize("case", [(40000, 120000, 5, "hits"), (150000, 1500000, 7, "pairs")])
-def test_partition_kernels_world2(tmp_path, oracle_mod, case):
+@pytest.mark.parametrize("case,peel_mode", [((40000, 120000, 5, "hits"), "partitioned"), ((150000, 1500000, 7, "pairs"), "partitioned"),
+                                            ((40000, 120000, 5, "hits"), "gather"), ((150000, 1500000, 7, "pairs"), "auto")])
+def test_partition_kernels_world2(tmp_path, oracle_mod, case, peel_mode):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), case), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), case, peel_mode), nprocs=2, join=True)
     parts = [pickle.load(open(tmp_path / f"rank{r}.pkl", "rb")) for r in range(2)]
     _check(parts, _expected(oracle_mod, case))
-    assert parts[0]["stats"]["exchange_subrounds"] > 0
+    if peel_mode == "partitioned":
+        assert parts[0]["stats"]["exchange_subrounds"] > 0
+    else:
+        assert parts[0]["stats"]["peel_mode"] == "gather"
