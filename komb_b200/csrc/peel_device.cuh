@@ -16,6 +16,7 @@ constexpr int kBatch = 64;           // adjacency ranges one traversal covers
 constexpr int kUnroll = 4;           // independent edge chains per thread (memory-level parallelism)
 constexpr uint32_t kSplit = 4096;    // rows longer than this are cut into slices shared by all CTAs
 constexpr int kSliceLenBits = 20;    // slice entry = first_edge << 20 | length
+constexpr uint32_t kDirectEdges = kPeelThreads * kUnroll;  // batches up to this size skip the degree pre-load
 constexpr int kScanItems = 8;        // alive-list entries per thread per scan tile
 constexpr int kScanTileV = kPeelThreads * kScanItems;
 
@@ -81,6 +82,7 @@ __device__ __forceinline__ void traverse_batch(const uint32_t total, const int32
                                                int32_t *deg, uint32_t *next, uint32_t *F, uint32_t *front_cnt,
                                                BlockShared &sh, uint32_t &overflowed, const PartView &part) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
+    const bool direct = total <= kDirectEdges;
     for (uint32_t base = 0; base < total; base += kPeelThreads * kUnroll) {
         uint32_t u[kUnroll];
         int32_t d[kUnroll];
@@ -116,15 +118,27 @@ __device__ __forceinline__ void traverse_batch(const uint32_t total, const int32
                 u[t] = (valid && !remote) ? loc : kFullMask;
             }
         }
+        if (direct) {
+            // latency-bound batch (one iteration): no degree pre-load, the decrement goes out right away and
+            // is undone if it lands at or below k -- one dependent round trip less on the cascade's critical path
 #pragma unroll
-        for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? __ldcg(&deg[u[t]]) : INT32_MIN;
+            for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? atomicSub(&deg[u[t]], 1) : INT32_MAX;
 #pragma unroll
-        for (int t = 0; t < kUnroll; ++t) {
-            push[t] = false;
-            if (d[t] > k) {
-                const int32_t old = atomicSub(&deg[u[t]], 1);
-                if (old == k + 1) push[t] = true;             // u just reached level k: ours to peel
-                else if (old <= k) atomicAdd(&deg[u[t]], 1);  // already at level k: undo (clamp)
+            for (int t = 0; t < kUnroll; ++t) {
+                push[t] = d[t] == k + 1;
+                if (d[t] <= k) atomicAdd(&deg[u[t]], 1);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? __ldcg(&deg[u[t]]) : INT32_MIN;
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) {
+                push[t] = false;
+                if (d[t] > k) {
+                    const int32_t old = atomicSub(&deg[u[t]], 1);
+                    if (old == k + 1) push[t] = true;             // u just reached level k: ours to peel
+                    else if (old <= k) atomicAdd(&deg[u[t]], 1);  // already at level k: undo (clamp)
+                }
             }
         }
 #pragma unroll
