@@ -216,14 +216,20 @@ def run_ours(args):
         g.close()
         return st
 
+    # page-locked result buffers, allocated once (as a long-running host would)
+    e_cap = int(2.2 * n_hits)
+    pin = {"u": ctx.pinned_empty(e_cap, np.uint32), "v": ctx.pinned_empty(e_cap, np.uint32),
+           "core": ctx.pinned_empty(N_UNITIGS, np.int32), "deg": ctx.pinned_empty(N_UNITIGS, np.int32),
+           "score": ctx.pinned_empty(N_UNITIGS, np.float64)}
+
     def step_e2e():
-        """The call a user of the C ABI makes: host hits in, every output the
-        komb2 host writes to its three files back on the host."""
+        """The call a user of the C ABI makes: host hits in (page-locked), every output the
+        komb2 host writes to its three files back on the host (page-locked)."""
         g = ctx.build_graph(rk_h.numpy().view(np.uint32), ut_h.numpy().view(np.uint32), N_UNITIGS)
-        core = g.coreness()
-        score = g.corea(komb_b200.KEY_REF32)
-        deg = g.degree()
-        u, v = g.edges()
+        core = g.coreness(out=pin["core"])
+        score = g.corea(komb_b200.KEY_REF32, out=pin["score"])
+        deg = g.degree(out=pin["deg"])
+        u, v = g.edges(out=(pin["u"], pin["v"]))
         st = g.stats()
         g.close()
         return st, (u.nbytes + v.nbytes + core.nbytes + deg.nbytes + score.nbytes)

@@ -89,6 +89,12 @@ int kombgpu_ctx_reset_stream(kombgpu_ctx *ctx);
  * the last error of a failed kombgpu_ctx_create on this thread. */
 const char *kombgpu_last_error(const kombgpu_ctx *ctx);
 
+/* Page-locked host memory for the buffers a host passes to the copying entry
+ * points (hits in, edges / degree / coreness / score out): DMA at full PCIe rate
+ * instead of staged pageable copies.  A host without CUDA headers can use these. */
+int kombgpu_pinned_alloc(kombgpu_ctx *ctx, uint64_t bytes, void **out);
+int kombgpu_pinned_free(kombgpu_ctx *ctx, void *ptr);
+
 /* Number of this library's kernels launched through the context so far. */
 int kombgpu_ctx_launches(const kombgpu_ctx *ctx, uint64_t *launches);
 

@@ -42,6 +42,8 @@ SIGNATURES = {
     "kombgpu_last_error": (c_char_p, [c_void_p]),
     "kombgpu_ctx_trim": (c_int, [c_void_p]),
     "kombgpu_ctx_launches": (c_int, [c_void_p, POINTER(c_uint64)]),
+    "kombgpu_pinned_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p)]),
+    "kombgpu_pinned_free": (c_int, [c_void_p, c_void_p]),
     "kombgpu_build_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_build_graph_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_graph_from_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),

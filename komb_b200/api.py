@@ -45,9 +45,13 @@ class Context:
             raise KombGpuError(rc, self._lib.kombgpu_last_error(None).decode())
         self._h = h
         self.device = int(device)
+        self._pinned = []
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in self._pinned:
+                self._lib.kombgpu_pinned_free(self._h, p)
+            self._pinned = []
             self._lib.kombgpu_ctx_destroy(self._h)
             self._h = None
 
@@ -68,6 +72,16 @@ class Context:
 
     def reset_stream(self):
         self._check(self._lib.kombgpu_ctx_reset_stream(self._h))
+
+    def pinned_empty(self, count: int, dtype) -> np.ndarray:
+        """A page-locked numpy array (freed with the context): pass it as `out=` to the getters, or fill it
+        with hits, so that host<->device copies run at full PCIe rate."""
+        dt = np.dtype(dtype)
+        p = c_void_p()
+        self._check(self._lib.kombgpu_pinned_alloc(self._h, int(count) * dt.itemsize, byref(p)))
+        self._pinned.append(p)
+        buf = (ctypes.c_char * (max(int(count), 0) * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=int(count))
 
     def launches(self) -> int:
         """Kernels of libkombgpu launched through this context so far."""
@@ -152,9 +166,19 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_counts(self._h, byref(n), byref(m)))
         return n.value, m.value
 
-    def edges(self) -> tuple[np.ndarray, np.ndarray]:
+    @staticmethod
+    def _out(out, count, dtype):
+        if out is None:
+            return np.empty(count, dtype)
+        if out.dtype != np.dtype(dtype) or out.ndim != 1 or out.shape[0] < count or not out.flags.c_contiguous:
+            raise ValueError(f"out= must be a contiguous 1-D {np.dtype(dtype)} array of at least {count} elements")
+        return out[:count]
+
+    def edges(self, out=None) -> tuple[np.ndarray, np.ndarray]:
+        """Canonical edge list; `out=(u_buf, v_buf)` reuses caller (e.g. page-locked) buffers."""
         _, m = self.counts()
-        u, v = np.empty(m, np.uint32), np.empty(m, np.uint32)
+        u = self._out(out[0] if out else None, m, np.uint32)
+        v = self._out(out[1] if out else None, m, np.uint32)
         self._ctx._check(self._lib.kombgpu_graph_edges(self._h, _ptr(u), _ptr(v)))
         return u, v
 
@@ -164,27 +188,27 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_csr(self._h, _ptr(row_ptr), _ptr(col)))
         return row_ptr, col
 
-    def degree(self) -> np.ndarray:
+    def degree(self, out=None) -> np.ndarray:
         n, _ = self.counts()
-        d = np.empty(n, np.int32)
+        d = self._out(out, n, np.int32)
         self._ctx._check(self._lib.kombgpu_degree(self._h, _ptr(d)))
         return d
 
-    def coreness(self, copy: bool = True):
+    def coreness(self, copy: bool = True, out=None):
         n, _ = self.counts()
         if not copy:
             self._ctx._check(self._lib.kombgpu_coreness(self._h, None))
             return None
-        c = np.empty(n, np.int32)
+        c = self._out(out, n, np.int32)
         self._ctx._check(self._lib.kombgpu_coreness(self._h, _ptr(c)))
         return c
 
-    def corea(self, key_mode: int = KEY_REF32, copy: bool = True):
+    def corea(self, key_mode: int = KEY_REF32, copy: bool = True, out=None):
         n, _ = self.counts()
         if not copy:
             self._ctx._check(self._lib.kombgpu_graph_corea(self._h, int(key_mode), None))
             return None
-        s = np.empty(n, np.float64)
+        s = self._out(out, n, np.float64)
         self._ctx._check(self._lib.kombgpu_graph_corea(self._h, int(key_mode), _ptr(s)))
         return s
 

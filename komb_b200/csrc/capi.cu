@@ -236,6 +236,24 @@ int kombgpu_ctx_reset_stream(kombgpu_ctx *ctx) {
 
 const char *kombgpu_last_error(const kombgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int kombgpu_pinned_alloc(kombgpu_ctx *ctx, uint64_t bytes, void **out) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if (!out) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    *out = nullptr;
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return ctx_fail(ctx, KOMBGPU_ENOMEM, "cannot page-lock %llu bytes of host memory", (unsigned long long)bytes);
+    }
+    return KOMBGPU_OK;
+}
+
+int kombgpu_pinned_free(kombgpu_ctx *ctx, void *ptr) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if (ptr) KG_CUDA(ctx, cudaFreeHost(ptr));
+    return KOMBGPU_OK;
+}
+
 int kombgpu_ctx_launches(const kombgpu_ctx *ctx, uint64_t *launches) {
     if (!ctx || !launches) return KOMBGPU_EINVAL;
     *launches = ctx->launches;

@@ -181,3 +181,19 @@ def test_device_resident_inputs(ctx, oracle_mod):
         g.analyse()
         arr = g.device_arrays()
         assert all(arr[k] for k in ("row_ptr", "col", "edges_packed", "degree", "coreness", "score"))
+
+
+def test_pinned_out_buffers(ctx, oracle_mod):
+    u, v = synth.rmat_edges(12, 40000, n_vertices=3000, seed=4)
+    exp_edges = oracle_mod.simplify(u, v)
+    bu, bv = ctx.pinned_empty(50000, np.uint32), ctx.pinned_empty(50000, np.uint32)
+    bc, bs = ctx.pinned_empty(3000, np.int32), ctx.pinned_empty(3000, np.float64)
+    with ctx.graph_from_edges(u, v, 3000) as g:
+        gu, gv = g.edges(out=(bu, bv))
+        assert gu.base is not None and np.array_equal(oracle_mod.pack_edges(gu, gv), exp_edges)
+        core = g.coreness(out=bc)
+        assert np.array_equal(core, oracle_mod.coreness(3000, exp_edges)[1])
+        s = g.corea(out=bs)
+        assert s.shape == (3000,) and np.all(s >= 0)
+        with pytest.raises(ValueError):
+            g.degree(out=np.empty(10, np.int32))
