@@ -334,7 +334,7 @@ int kombgpu_part_peel_begin(kombgpu_part *p) {
         if (!*slot) *slot = ws_alloc(ctx, bytes);
         return *slot != nullptr;
     };
-    const uint64_t slice_cap = 2 * p->n_directed / kSplit + 64;
+    const uint64_t slice_cap = p->n_directed / kSliceLen + p->n_directed / kSplit + 64;
     bool ok = need((void **)&p->core, n * sizeof(int32_t)) && need((void **)&p->frontier, n * sizeof(uint32_t)) &&
               need((void **)&p->alive[0], n * sizeof(uint32_t)) && need((void **)&p->alive[1], n * sizeof(uint32_t)) &&
               need((void **)&p->outbox, (p->n_directed ? p->n_directed : 1) * sizeof(uint32_t)) &&

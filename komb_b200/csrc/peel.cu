@@ -22,7 +22,9 @@
 // Empty levels are skipped through a min-reduction of the survivors' degrees
 // done by the scan itself.  The peel is bound by its dependency depth (levels x
 // cascade sub-rounds), not by bytes: see DESIGN.md "Peel".
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "peel_device.cuh"
 
@@ -83,6 +85,11 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         n_alive = survivors;
         ++round;
 
+        const uint32_t trace_row = round - 1;
+        if (prof && st->trace && trace_row < st->trace_cap) {
+            unsigned long long *tr = st->trace + 6ull * trace_row;
+            tr[0] = (unsigned long long)(uint32_t)k; tr[1] = front_hi; tr[2] = survivors; tr[3] = tp1 - tp0; tr[4] = 0; tr[5] = 0;
+        }
         if (front_hi == 0) {
             // empty level: nothing to process; jump to the smallest remaining degree
             if (survivors == 0 || min_next == INT32_MAX) break;
@@ -104,7 +111,12 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
             unsigned long long tp3 = prof ? global_ns() : 0;
             if (prof) st->subrounds += 1;
             grid.sync();
-            if (prof) { st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += global_ns() - tp3; tp2 = global_ns(); }
+            if (prof) {
+                const unsigned long long tp4 = global_ns();
+                st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += tp4 - tp3;
+                if (st->trace && trace_row < st->trace_cap) { st->trace[6ull * trace_row + 4] += tp3 - tp2; st->trace[6ull * trace_row + 5] += tp4 - tp3; }
+                tp2 = tp4;
+            }
             front_lo = front_hi;
             slice_lo = slice_hi;
             front_hi = __ldcg(&st->front_cnt[par]);  // stable: nothing appends between sub-rounds
@@ -139,7 +151,7 @@ int peel_coreness(kombgpu_graph *g) {
     DevBuf<uint64_t> slices;
     DevBuf<PeelState> state(ctx, 1);
     // a row is sliced at most once: <= 2E/kSplit long rows, each giving <= len/kSplit + 1 slices
-    const uint64_t slice_cap = 4 * g->n_edges / kSplit + 64;
+    const uint64_t slice_cap = 2 * g->n_edges / kSliceLen + 2 * g->n_edges / kSplit + 64;
     if (slice_cap >= 0xffffffffull || 2 * g->n_edges >= (1ull << (64 - kSliceLenBits)))
         return ctx_fail(ctx, KOMBGPU_EINVAL, "graph too large for the slice encoding");
     KG_ALLOC(ctx, slices, slice_cap);
@@ -149,6 +161,15 @@ int peel_coreness(kombgpu_graph *g) {
     if (!state) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
     PeelState init{};
     for (int i = 0; i < 3; ++i) init.next_min[i] = INT32_MAX;
+    DevBuf<unsigned long long> trace;
+    const char *trace_path = getenv("KOMBGPU_TRACE");
+    const uint32_t trace_cap = 1u << 16;
+    if (trace_path) {
+        KG_ALLOC(ctx, trace, 6ull * trace_cap);
+        KG_CUDA(ctx, cudaMemsetAsync(trace.p, 0, 6ull * trace_cap * sizeof(unsigned long long), ctx->stream));
+        init.trace = trace.p;
+        init.trace_cap = trace_cap;
+    }
     KG_CUDA(ctx, cudaMemcpyAsync(state.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
 
     uint32_t n_arg = n;
@@ -178,6 +199,17 @@ int peel_coreness(kombgpu_graph *g) {
         fprintf(stderr, "[kombgpu] peel n=%u levels=%u rounds=%u subrounds=%u grid=%d kernel=%.3f ms | cta0: scan %.3f ms, sync1 %.3f ms, process %.3f ms, sync2 %.3f ms | batches %llu overflow %llu slices %llu\n",
                 n, fin.levels, fin.rounds, fin.subrounds, grid, g->st.ms_peel_kernel, fin.prof_ns[0] * 1e-6, fin.prof_ns[1] * 1e-6,
                 fin.prof_ns[2] * 1e-6, fin.prof_ns[3] * 1e-6, fin.batches, fin.overflowed, fin.sliced);
+    if (trace_path) {
+        const uint32_t rows = fin.rounds < trace_cap ? fin.rounds : trace_cap;
+        std::vector<unsigned long long> h(6ull * rows);
+        KG_CUDA(ctx, cudaMemcpy(h.data(), trace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(trace_path, "w")) {
+            fprintf(f, "round,k,frontier,survivors,scan_ns,process_ns,wait_ns\n");
+            for (uint32_t r = 0; r < rows; ++r)
+                fprintf(f, "%u,%llu,%llu,%llu,%llu,%llu,%llu\n", r, h[6 * r], h[6 * r + 1], h[6 * r + 2], h[6 * r + 3], h[6 * r + 4], h[6 * r + 5]);
+            fclose(f);
+        }
+    }
     if (fin.error) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel invariant broken (code %u, %llu of %u vertices peeled)", fin.error, fin.n_removed, n);
     if (fin.n_removed != n) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel ended with %llu of %u vertices peeled", fin.n_removed, n);
     g->st.max_coreness = fin.max_core;

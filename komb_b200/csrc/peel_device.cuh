@@ -14,7 +14,8 @@ constexpr int kPeelWarps = kPeelThreads / 32;
 constexpr int kLocalQ = 2048;        // capacity of each CTA-local vertex list (two lists: current, next)
 constexpr int kBatch = 64;           // adjacency ranges one traversal covers
 constexpr int kUnroll = 4;           // independent edge chains per thread (memory-level parallelism)
-constexpr uint32_t kSplit = 4096;    // rows longer than this are cut into slices shared by all CTAs
+constexpr uint32_t kSplit = 2048;    // rows longer than this are cut into slices shared by all CTAs
+constexpr uint32_t kSliceLen = 2048; // edges per slice: one traversal iteration of a CTA
 constexpr int kSliceLenBits = 20;    // slice entry = first_edge << 20 | length
 constexpr uint32_t kDirectEdges = kPeelThreads * kUnroll;  // batches up to this size skip the degree pre-load
 constexpr int kScanItems = 8;        // alive-list entries per thread per scan tile
@@ -43,6 +44,8 @@ struct PeelState {
     // CTA 0's view of where the time goes (ns): scan, barrier after scan, process, barrier after process
     unsigned long long prof_ns[4];
     unsigned long long batches;    // traversals over all CTAs
+    unsigned long long *trace;     // optional (KOMBGPU_TRACE): 6 words per round, CTA 0's view
+    uint32_t trace_cap;
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -234,10 +237,13 @@ __device__ __forceinline__ uint32_t process_subround(const int32_t k, uint32_t *
 
     // ---- slices: kBatch of them per traversal, dealt round-robin ----
     const uint32_t n_slices = s_hi - s_lo;
-    for (uint32_t g0 = blockIdx.x * kBatch; g0 < n_slices; g0 += gridDim.x * kBatch) {
+    // as many slices per traversal as keeps every CTA busy: a tail level has a few dozen slices, and
+    // dealing them kBatch at a time would serialise them on one or two CTAs
+    const uint32_t slice_sz = min((uint32_t)kBatch, max(1u, (n_slices + gridDim.x - 1) / gridDim.x));
+    for (uint32_t g0 = blockIdx.x * slice_sz; g0 < n_slices; g0 += gridDim.x * slice_sz) {
         uint32_t my_len = 0;
         uint64_t my_row = 0;
-        if (tid < kBatch && g0 + tid < n_slices) {
+        if (tid < slice_sz && g0 + tid < n_slices) {
             const uint64_t e = __ldcg(&S[s_lo + g0 + tid]);
             my_row = e >> kSliceLenBits;
             my_len = (uint32_t)(e & ((1u << kSliceLenBits) - 1));
@@ -257,7 +263,7 @@ __device__ __forceinline__ uint32_t process_subround(const int32_t k, uint32_t *
     const uint32_t chunk_sz = min((uint32_t)kBatch, max(1u, (n_front + gridDim.x - 1) / gridDim.x));
     const uint32_t n_chunks = (n_front + chunk_sz - 1) / chunk_sz;
     // start dealing where the slices stopped, so that CTA 0 does not get the first share of both
-    uint32_t chunk = (blockIdx.x + gridDim.x - (n_slices / kBatch) % gridDim.x) % gridDim.x;
+    uint32_t chunk = (blockIdx.x + gridDim.x - ((n_slices + slice_sz - 1) / slice_sz) % gridDim.x) % gridDim.x;
     while (true) {
         uint32_t n_cur = min(sh.next_cnt, (uint32_t)kLocalQ);
         __syncthreads();  // everyone has read next_cnt
@@ -284,10 +290,10 @@ __device__ __forceinline__ uint32_t process_subround(const int32_t k, uint32_t *
                 my_len = (uint32_t)(row_ptr[v + 1] - my_row);
                 if (my_len > kSplit) {
                     // hub row: hand it to the whole grid as slices of the next sub-round
-                    const uint32_t n_sl = (my_len + kSplit - 1) / kSplit;
+                    const uint32_t n_sl = (my_len + kSliceLen - 1) / kSliceLen;
                     const uint32_t s0 = atomicAdd(slice_cnt, n_sl);
                     for (uint32_t i = 0; i < n_sl; ++i)
-                        S[s0 + i] = ((my_row + (uint64_t)i * kSplit) << kSliceLenBits) | min(kSplit, my_len - i * kSplit);
+                        S[s0 + i] = ((my_row + (uint64_t)i * kSliceLen) << kSliceLenBits) | min(kSliceLen, my_len - i * kSliceLen);
                     sliced += n_sl;
                     my_len = 0;
                 }
