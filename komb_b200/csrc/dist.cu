@@ -36,8 +36,9 @@ struct kombgpu_part {
     int32_t *deg = nullptr;       // [n_local]
     int32_t *core = nullptr;      // [n_local] working degrees / coreness
     // peel state
-    uint32_t *frontier = nullptr, *alive[2] = {nullptr, nullptr}, *outbox = nullptr;
-    uint64_t *slices = nullptr;
+    uint32_t *alive[2] = {nullptr, nullptr}, *outbox = nullptr;
+    uint64_t *pool = nullptr;     // task pool of the peel (peel_device.cuh)
+    uint32_t pool_cap = 0;
     kg::peel::PeelState *state = nullptr;
     uint32_t *counters = nullptr;  // [4]: outbox_cnt, front_cnt (apply), spare, spare
     uint32_t n_alive = 0;
@@ -45,6 +46,7 @@ struct kombgpu_part {
     uint32_t n_front = 0;          // entries waiting in `frontier`
     uint32_t n_outbox = 0;
     int grid = 0;
+    uint32_t round = 0;            // process launches so far (names the level token)
 };
 
 namespace kg {
@@ -55,41 +57,33 @@ constexpr int kThreads = 256;
 
 // level-k scan of one rank (stand-alone launch; state slot 0 holds the results)
 __global__ void __launch_bounds__(kPeelThreads) part_scan_kernel(int32_t k, const uint32_t *alive_src, uint32_t n_alive,
-                                                                 uint32_t *alive_dst, const int32_t *deg, uint32_t *F,
+                                                                 uint32_t *alive_dst, const int32_t *deg, uint64_t *Q,
                                                                  PeelState *st) {
     __shared__ BlockShared sh;
-    int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, F, &st->front_cnt[0], &st->alive_out[0], sh);
+    int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, Q, &st->q_tail, &st->front_cnt[0], &st->alive_out[0], sh);
     local_min = warp_reduce_min(local_min);
     if (lane_id() == 0 && local_min != INT32_MAX) atomicMin(&st->next_min[0], local_min);
 }
 
-// local PROCESS of level k: the frontier list [0, n_front) and, in follow-up sub-rounds, hub slices and
-// CTA-list overflow.  Cooperative: sub-rounds are separated by grid barriers.
-__global__ void __launch_bounds__(kPeelThreads) part_process_kernel(int32_t k, uint32_t n_front,
+// local PROCESS of level k: everything in the pool (frontier from the scan or from part_apply_kernel) plus the
+// local cascade it triggers.  Cooperative (all CTAs resident: they hand work to one another through the pool).
+__global__ void __launch_bounds__(kPeelThreads) part_process_kernel(int32_t k, uint32_t round,
                                                                     const uint64_t *__restrict__ row_ptr,
                                                                     const uint32_t *__restrict__ col, int32_t *deg,
-                                                                    uint32_t *F, uint64_t *S, PeelState *st, PartView part) {
+                                                                    uint64_t *Q, uint32_t cap, PeelState *st, PartView part) {
     cg::grid_group grid = cg::this_grid();
     __shared__ BlockShared sh;
-    uint32_t removed = 0;
-    uint32_t front_lo = 0, front_hi = n_front, slice_lo = 0, slice_hi = 0;
-    while (front_lo < front_hi || slice_lo < slice_hi) {
-        removed += process_subround<true>(k, F, front_lo, front_hi, &st->front_cnt[0], S, slice_lo, slice_hi,
-                                          &st->slice_cnt[0], row_ptr, col, deg, st, sh, part);
-        grid.sync();
-        front_lo = front_hi;
-        slice_lo = slice_hi;
-        front_hi = __ldcg(&st->front_cnt[0]);
-        slice_hi = __ldcg(&st->slice_cnt[0]);
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->subrounds += 1;
-    }
+    const uint32_t removed = process_level<true>(k, round, Q, cap, row_ptr, col, deg, st, sh, part);
     if (threadIdx.x == 0 && removed) atomicAdd(&st->n_removed, (unsigned long long)removed);
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->q_head = __ldcg(&st->q_done);  // un-reserve the slots past the tail
 }
 
-// decrements that arrived from other ranks (global ids of vertices this rank owns)
+// decrements that arrived from other ranks (global ids of vertices this rank owns); vertices that reach k
+// are appended to the pool
 __global__ void __launch_bounds__(kThreads) part_apply_kernel(int32_t k, const uint32_t *__restrict__ recv, uint64_t count,
-                                                              uint32_t v_lo, uint32_t n_local, int32_t *deg, uint32_t *F,
-                                                              uint32_t *front_cnt, uint32_t *error) {
+                                                              uint32_t v_lo, uint32_t n_local, int32_t *deg, uint64_t *Q,
+                                                              uint32_t cap, PeelState *st, uint32_t *front_cnt) {
     const uint32_t lane = lane_id();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
@@ -99,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) part_apply_kernel(int32_t k, const u
         if (i < count) {
             loc = recv[i] - v_lo;
             if (loc >= n_local) {
-                atomicExch(error, 5u);
+                atomicExch(&st->error, 5u);
             } else if (__ldcg(&deg[loc]) > k) {
                 const int32_t old = atomicSub(&deg[loc], 1);
                 if (old == k + 1) push = true;
@@ -109,9 +103,12 @@ __global__ void __launch_bounds__(kThreads) part_apply_kernel(int32_t k, const u
         const uint32_t pm = __ballot_sync(kFullMask, push);
         if (pm) {
             uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(front_cnt, (uint32_t)__popc(pm));
+            if (lane == 0) { pos = atomicAdd(&st->q_tail, (uint32_t)__popc(pm)); atomicAdd(front_cnt, (uint32_t)__popc(pm)); }
             pos = __shfl_sync(kFullMask, pos, 0) + __popc(pm & lanemask_lt());
-            if (push) F[pos] = loc;
+            if (push) {
+                if (pos < cap) Q[pos] = (uint64_t)loc;
+                else atomicExch(&st->error, 3u);
+            }
         }
     }
 }
@@ -185,7 +182,7 @@ int make_bounds(kombgpu_ctx *ctx, const uint32_t *bounds, int n_parts, Bounds *o
 
 void part_release(kombgpu_part *p) {
     kombgpu_ctx *ctx = p->ctx;
-    void *ptrs[] = {p->row_ptr, p->col, p->deg, p->core, p->frontier, p->alive[0], p->alive[1], p->outbox, p->slices, p->state, p->counters};
+    void *ptrs[] = {p->row_ptr, p->col, p->deg, p->core, p->alive[0], p->alive[1], p->outbox, p->pool, p->state, p->counters};
     for (void *q : ptrs) if (q) ws_free(ctx, q);
 }
 
@@ -334,25 +331,29 @@ int kombgpu_part_peel_begin(kombgpu_part *p) {
         if (!*slot) *slot = ws_alloc(ctx, bytes);
         return *slot != nullptr;
     };
-    const uint64_t slice_cap = p->n_directed / kSliceLen + p->n_directed / kSplit + 64;
-    bool ok = need((void **)&p->core, n * sizeof(int32_t)) && need((void **)&p->frontier, n * sizeof(uint32_t)) &&
+    int per_sm = 0;
+    KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, part_process_kernel, kPeelThreads, 0));
+    if (per_sm < 1) return ctx_fail(ctx, KOMBGPU_ECUDA, "partition peel kernel does not fit on an SM");
+    p->grid = per_sm * ctx->sm_count;
+    // every local vertex enters the pool at most once, every long row is sliced at most once, plus reserved slots
+    const uint64_t cap64 = (uint64_t)p->n_local + p->n_directed / kSliceLen + p->n_directed / kSplit + (uint64_t)p->grid * kClaimMax + 64;
+    if (cap64 >= 0xffffffffull || p->n_directed >= (1ull << (63 - kSliceLenBits)))
+        return ctx_fail(ctx, KOMBGPU_EINVAL, "partition too large for the pool encoding");
+    p->pool_cap = (uint32_t)cap64;
+    bool ok = need((void **)&p->core, n * sizeof(int32_t)) && need((void **)&p->pool, (size_t)p->pool_cap * sizeof(uint64_t)) &&
               need((void **)&p->alive[0], n * sizeof(uint32_t)) && need((void **)&p->alive[1], n * sizeof(uint32_t)) &&
               need((void **)&p->outbox, (p->n_directed ? p->n_directed : 1) * sizeof(uint32_t)) &&
-              need((void **)&p->slices, slice_cap * sizeof(uint64_t)) && need((void **)&p->state, sizeof(PeelState)) &&
-              need((void **)&p->counters, 4 * sizeof(uint32_t));
+              need((void **)&p->state, sizeof(PeelState)) && need((void **)&p->counters, 4 * sizeof(uint32_t));
     if (!ok) return ctx_fail(ctx, KOMBGPU_ENOMEM, "partition peel state");
-    if (p->n_directed >= (1ull << (64 - kSliceLenBits))) return ctx_fail(ctx, KOMBGPU_EINVAL, "partition too large for the slice encoding");
     KG_CUDA(ctx, cudaMemcpyAsync(p->core, p->deg, p->n_local * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    KG_CUDA(ctx, cudaMemsetAsync(p->pool, 0xff, (size_t)p->pool_cap * sizeof(uint64_t), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(p->state, 0, sizeof(PeelState), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(p->counters, 0, 4 * sizeof(uint32_t), ctx->stream));
     p->n_alive = p->n_local;
     p->alive_cur = -1;
     p->n_front = 0;
     p->n_outbox = 0;
-    int per_sm = 0;
-    KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, part_process_kernel, kPeelThreads, 0));
-    if (per_sm < 1) return ctx_fail(ctx, KOMBGPU_ECUDA, "partition peel kernel does not fit on an SM");
-    p->grid = per_sm * ctx->sm_count;
+    p->round = 0;
     return KOMBGPU_OK;
 }
 
@@ -360,23 +361,18 @@ int kombgpu_part_peel_scan(kombgpu_part *p, int32_t k, uint32_t *n_front, uint32
     if (!p || !p->state) return KOMBGPU_EINVAL;
     kombgpu_ctx *ctx = p->ctx;
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
-    PeelState init{};
-    init.next_min[0] = INT32_MAX;
-    // keep the run-long counters, reset the per-scan slot
+    // reset the per-scan slot, keep the pool counters and the run-long statistics
     PeelState cur{};
     KG_TRY(read_back(ctx, p->state, &cur, 1));
-    init.n_removed = cur.n_removed;
-    init.subrounds = cur.subrounds;
-    init.overflowed = cur.overflowed;
-    init.sliced = cur.sliced;
-    init.batches = cur.batches;
-    init.error = cur.error;
-    KG_CUDA(ctx, cudaMemcpyAsync(p->state, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    cur.alive_out[0] = 0;
+    cur.front_cnt[0] = 0;
+    cur.next_min[0] = INT32_MAX;
+    KG_CUDA(ctx, cudaMemcpyAsync(p->state, &cur, sizeof(cur), cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t *src = p->alive_cur < 0 ? nullptr : p->alive[p->alive_cur];
     const int dst_i = p->alive_cur < 0 ? 0 : (p->alive_cur ^ 1);
     if (p->n_alive) {
         uint32_t grid = min(ceil_div_u64(p->n_alive, kScanTileV), (uint32_t)p->grid);
-        KG_LAUNCH(ctx, part_scan_kernel, grid, kPeelThreads, 0, k, src, p->n_alive, p->alive[dst_i], p->core, p->frontier, p->state);
+        KG_LAUNCH(ctx, part_scan_kernel, grid, kPeelThreads, 0, k, src, p->n_alive, p->alive[dst_i], p->core, p->pool, p->state);
     }
     PeelState res{};
     KG_TRY(read_back(ctx, p->state, &res, 1));
@@ -395,31 +391,30 @@ int kombgpu_part_peel_process(kombgpu_part *p, int32_t k, uint32_t *n_outbox) {
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
     p->n_outbox = 0;
     if (p->n_front) {
-        // front_cnt[0] = list length (overflow appends past it), slice_cnt[0] = 0, outbox empty
-        uint32_t zero4[4] = {0, 0, 0, 0};
-        KG_CUDA(ctx, cudaMemcpyAsync(p->counters, zero4, sizeof(zero4), cudaMemcpyHostToDevice, ctx->stream));
-        KG_CUDA(ctx, cudaMemcpyAsync(&p->state->front_cnt[0], &p->n_front, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        KG_CUDA(ctx, cudaMemsetAsync(&p->state->slice_cnt[0], 0, sizeof(uint32_t), ctx->stream));
+        KG_CUDA(ctx, cudaMemsetAsync(p->counters, 0, 4 * sizeof(uint32_t), ctx->stream));  // outbox empty
         PartView pv;
         pv.v_lo = p->v_lo;
         pv.n_local = p->n_local;
         pv.outbox = p->outbox;
         pv.outbox_cnt = &p->counters[0];
         int32_t k_arg = k;
-        uint32_t nf = p->n_front;
+        uint32_t round = ++p->round;
         const uint64_t *row_ptr = p->row_ptr;
         const uint32_t *col = p->col;
         int32_t *deg = p->core;
-        uint32_t *F = p->frontier;
-        uint64_t *S = p->slices;
+        uint64_t *Q = p->pool;
+        uint32_t cap = p->pool_cap;
         PeelState *st = p->state;
-        void *args[] = {&k_arg, &nf, &row_ptr, &col, &deg, &F, &S, &st, &pv};
+        void *args[] = {&k_arg, &round, &row_ptr, &col, &deg, &Q, &cap, &st, &pv};
         KG_CUDA(ctx, cudaLaunchCooperativeKernel((void *)part_process_kernel, dim3(p->grid), dim3(kPeelThreads), args, 0, ctx->stream));
         ctx->launches++;
         uint32_t c[4];
         KG_TRY(read_back(ctx, p->counters, c, 4));
         p->n_outbox = c[0];
         p->n_front = 0;
+        uint32_t err = 0;
+        KG_TRY(read_back(ctx, &p->state->error, &err, 1));
+        if (err) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "partition peel invariant broken (code %u)", err);
     }
     if (n_outbox) *n_outbox = p->n_outbox;
     return KOMBGPU_OK;
@@ -462,8 +457,8 @@ int kombgpu_part_peel_apply_dev(kombgpu_part *p, int32_t k, const uint32_t *recv
     if (count) {
         KG_CUDA(ctx, cudaMemsetAsync(&p->counters[1], 0, sizeof(uint32_t), ctx->stream));
         const uint32_t grid = min(ceil_div_u64(count, kThreads), (uint32_t)ctx->sm_count * 8u);
-        KG_LAUNCH(ctx, part_apply_kernel, grid, kThreads, 0, k, recv, count, p->v_lo, p->n_local, p->core, p->frontier,
-                  &p->counters[1], &p->state->error);
+        KG_LAUNCH(ctx, part_apply_kernel, grid, kThreads, 0, k, recv, count, p->v_lo, p->n_local, p->core, p->pool, p->pool_cap,
+                  p->state, &p->counters[1]);
         uint32_t c[4];
         KG_TRY(read_back(ctx, p->counters, c, 4));
         p->n_front = c[1];

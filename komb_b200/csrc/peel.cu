@@ -5,23 +5,24 @@
 // in HashIndexedMinHeap.h.  Coreness is a unique function of the simple graph,
 // so the result is bit-exact against any correct implementation.
 //
-// One persistent cooperative kernel peels the whole graph (PKC-style):
+// One persistent cooperative kernel peels the whole graph:
 //   level k:  SCAN     one pass over the compacted alive list: vertices with
-//                      deg == k form the level's frontier list, vertices above k
-//                      are compacted (CTA-wide scan, two global atomics per tile)
-//             PROCESS  the frontier is dealt to the CTAs round-robin; a CTA walks
-//                      its rows edge-parallel: for each neighbour u with
-//                      deg[u] > k: atomicSub(deg[u]); the thread that takes it to
-//                      k owns u and pushes it (ballot/popc aggregated) to the
-//                      CTA's own shared-memory list, processed next by the same
-//                      CTA, so the level-k cascade needs no grid-wide barrier and
-//                      no global queue; a decrement that lands below k is undone,
-//                      so deg[] is clamped at k and the final deg[] IS the coreness.
-//                      Hub rows are cut into slices that all CTAs share in a
-//                      follow-up sub-round.
+//                      deg == k are appended to the task pool, vertices above k
+//                      are compacted (CTA-wide scan, three global atomics per tile)
+//             PROCESS  CTAs claim pool entries (fetch-add tickets) and walk the
+//                      rows edge-parallel: for each neighbour u with deg[u] > k:
+//                      atomicSub(deg[u]); the thread that takes it to k owns u and
+//                      pushes it (ballot/popc aggregated) to the CTA's own
+//                      shared-memory list, processed next by the same CTA, so a
+//                      cascade chain needs no grid barrier and no global queue; a
+//                      decrement that lands below k is undone, so deg[] is clamped
+//                      at k and the final deg[] IS the coreness.  A CTA that
+//                      discovers more than it can use shares the surplus through
+//                      the pool; hub rows go to the pool as slices; idle CTAs park
+//                      on reserved pool slots and are handed work with one store.
 // Empty levels are skipped through a min-reduction of the survivors' degrees
 // done by the scan itself.  The peel is bound by its dependency depth (levels x
-// cascade sub-rounds), not by bytes: see DESIGN.md "Peel".
+// cascade generations), not by bytes: see DESIGN.md "Peel" and peel_device.cuh.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -38,7 +39,7 @@ using namespace peel;
 
 __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const uint64_t *__restrict__ row_ptr,
                                                             const uint32_t *__restrict__ col, int32_t *deg,
-                                                            uint32_t *F, uint64_t *S, uint32_t *alive_a, uint32_t *alive_b,
+                                                            uint64_t *Q, uint32_t cap, uint32_t *alive_a, uint32_t *alive_b,
                                                             PeelState *st) {
     cg::grid_group grid = cg::this_grid();
     __shared__ BlockShared sh;
@@ -54,21 +55,17 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
     while (true) {
         const uint32_t par = round % 3;
         // ---------------- SCAN ----------------
-        // One pass over the alive list: vertices at deg == k go to the frontier list F,
-        // vertices above k are compacted into the next alive list, the rest (peeled at an
-        // earlier level) are dropped.  Tiles of kScanTileV entries; positions come from a
-        // CTA-wide scan, so each tile costs two global atomics in all.
         if (blockIdx.x == 0 && tid == 0) {  // re-arm the slot of the NEXT round
             const uint32_t nxt = (round + 1) % 3;
             st->alive_out[nxt] = 0;
             st->front_cnt[nxt] = 0;
-            st->slice_cnt[nxt] = 0;
             st->next_min[nxt] = INT32_MAX;
             st->rounds = round + 1;
         }
         const bool prof = (blockIdx.x == 0 && tid == 0);
         unsigned long long tp0 = prof ? global_ns() : 0;
-        int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, F, &st->front_cnt[par], &st->alive_out[par], sh);
+        int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, Q, &st->q_tail, &st->front_cnt[par],
+                                       &st->alive_out[par], sh);
         local_min = warp_reduce_min(local_min);
         if (lane == 0 && local_min != INT32_MAX) atomicMin(&st->next_min[par], local_min);
         unsigned long long tp1 = prof ? global_ns() : 0;
@@ -76,7 +73,7 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         unsigned long long tp2 = prof ? global_ns() : 0;
         if (prof) { st->prof_ns[0] += tp1 - tp0; st->prof_ns[1] += tp2 - tp1; }
 
-        uint32_t front_hi = __ldcg(&st->front_cnt[par]);
+        const uint32_t front_cnt = __ldcg(&st->front_cnt[par]);
         const uint32_t survivors = __ldcg(&st->alive_out[par]);
         const int32_t min_next = __ldcg(&st->next_min[par]);
         // the compacted list becomes the next scan's input
@@ -84,13 +81,12 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         alive_dst = (alive_dst == alive_a) ? alive_b : alive_a;
         n_alive = survivors;
         ++round;
-
         const uint32_t trace_row = round - 1;
         if (prof && st->trace && trace_row < st->trace_cap) {
             unsigned long long *tr = st->trace + 6ull * trace_row;
-            tr[0] = (unsigned long long)(uint32_t)k; tr[1] = front_hi; tr[2] = survivors; tr[3] = tp1 - tp0; tr[4] = 0; tr[5] = 0;
+            tr[0] = (unsigned long long)(uint32_t)k; tr[1] = front_cnt; tr[2] = survivors; tr[3] = tp1 - tp0; tr[4] = 0; tr[5] = 0;
         }
-        if (front_hi == 0) {
+        if (front_cnt == 0) {
             // empty level: nothing to process; jump to the smallest remaining degree
             if (survivors == 0 || min_next == INT32_MAX) break;
             k = min_next;
@@ -102,26 +98,17 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         }
 
         // ---------------- PROCESS ----------------
-        // sub-round 0 takes the scan's frontier; later ones take the slices of long rows and
-        // whatever overflowed the CTA-local lists
-        uint32_t front_lo = 0, slice_lo = 0, slice_hi = 0;
-        while (front_lo < front_hi || slice_lo < slice_hi) {
-            removed += process_subround<false>(k, F, front_lo, front_hi, &st->front_cnt[par], S, slice_lo, slice_hi,
-                                               &st->slice_cnt[par], row_ptr, col, deg, st, sh, PartView{});
-            unsigned long long tp3 = prof ? global_ns() : 0;
-            if (prof) st->subrounds += 1;
-            grid.sync();
-            if (prof) {
-                const unsigned long long tp4 = global_ns();
-                st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += tp4 - tp3;
-                if (st->trace && trace_row < st->trace_cap) { st->trace[6ull * trace_row + 4] += tp3 - tp2; st->trace[6ull * trace_row + 5] += tp4 - tp3; }
-                tp2 = tp4;
-            }
-            front_lo = front_hi;
-            slice_lo = slice_hi;
-            front_hi = __ldcg(&st->front_cnt[par]);  // stable: nothing appends between sub-rounds
-            slice_hi = __ldcg(&st->slice_cnt[par]);
+        removed += process_level<false>(k, round, Q, cap, row_ptr, col, deg, st, sh, PartView{});
+        unsigned long long tp3 = prof ? global_ns() : 0;
+        grid.sync();
+        if (prof) {
+            const unsigned long long tp4 = global_ns();
+            st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += tp4 - tp3;
+            if (st->trace && trace_row < st->trace_cap) { st->trace[6ull * trace_row + 4] = tp3 - tp2; st->trace[6ull * trace_row + 5] = tp4 - tp3; }
         }
+        // q_done == q_tail here and nothing moves until the next PROCESS phase
+        if (__ldcg(&st->error)) break;
+        if (blockIdx.x == 0 && tid == 0) st->q_head = __ldcg(&st->q_done);  // un-reserve the slots past the tail
         k += 1;
     }
     if (tid == 0 && removed) atomicAdd(&st->n_removed, (unsigned long long)removed);
@@ -147,15 +134,17 @@ int peel_coreness(kombgpu_graph *g) {
     if (per_sm < 1) return ctx_fail(ctx, KOMBGPU_ECUDA, "peel kernel does not fit on an SM");
     const int grid = per_sm * ctx->sm_count;  // persistent: every CTA resident (cooperative launch)
 
-    DevBuf<uint32_t> frontier, alive_a, alive_b;
-    DevBuf<uint64_t> slices;
+    DevBuf<uint32_t> alive_a, alive_b;
+    DevBuf<uint64_t> pool;
     DevBuf<PeelState> state(ctx, 1);
-    // a row is sliced at most once: <= 2E/kSplit long rows, each giving <= len/kSplit + 1 slices
-    const uint64_t slice_cap = 2 * g->n_edges / kSliceLen + 2 * g->n_edges / kSplit + 64;
-    if (slice_cap >= 0xffffffffull || 2 * g->n_edges >= (1ull << (64 - kSliceLenBits)))
-        return ctx_fail(ctx, KOMBGPU_EINVAL, "graph too large for the slice encoding");
-    KG_ALLOC(ctx, slices, slice_cap);
-    KG_ALLOC(ctx, frontier, n);   // every vertex enters a frontier list at most once
+    // every vertex enters the pool at most once; a row is sliced at most once (<= 2E/kSplit long rows, each giving
+    // <= len/kSliceLen + 1 slices); plus the slots idle CTAs reserve past the tail
+    const uint64_t cap64 = (uint64_t)n + 2 * g->n_edges / kSliceLen + 2 * g->n_edges / kSplit + (uint64_t)grid * kClaimMax + 64;
+    if (cap64 >= 0xffffffffull || 2 * g->n_edges >= (1ull << (63 - kSliceLenBits)))
+        return ctx_fail(ctx, KOMBGPU_EINVAL, "graph too large for the pool encoding");
+    const uint32_t cap = (uint32_t)cap64;
+    KG_ALLOC(ctx, pool, cap);
+    KG_CUDA(ctx, cudaMemsetAsync(pool.p, 0xff, (size_t)cap * sizeof(uint64_t), ctx->stream));
     KG_ALLOC(ctx, alive_a, n);
     KG_ALLOC(ctx, alive_b, n);
     if (!state) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
@@ -176,10 +165,11 @@ int peel_coreness(kombgpu_graph *g) {
     const uint64_t *row_ptr = g->row_ptr;
     const uint32_t *col = g->col;
     int32_t *core = g->core;
-    uint32_t *fr = frontier.p, *aa = alive_a.p, *ab = alive_b.p;
-    uint64_t *sl = slices.p;
+    uint32_t *aa = alive_a.p, *ab = alive_b.p;
+    uint64_t *q = pool.p;
+    uint32_t cap_arg = cap;
     PeelState *sp = state.p;
-    void *args[] = {&n_arg, &row_ptr, &col, &core, &fr, &sl, &aa, &ab, &sp};
+    void *args[] = {&n_arg, &row_ptr, &col, &core, &q, &cap_arg, &aa, &ab, &sp};
     cudaEvent_t ev0, ev1;
     KG_CUDA(ctx, cudaEventCreate(&ev0));
     KG_CUDA(ctx, cudaEventCreate(&ev1));
@@ -196,9 +186,9 @@ int peel_coreness(kombgpu_graph *g) {
     PeelState fin{};
     KG_TRY(read_back(ctx, state.p, &fin, 1));
     if (getenv("KOMBGPU_DEBUG"))
-        fprintf(stderr, "[kombgpu] peel n=%u levels=%u rounds=%u subrounds=%u grid=%d kernel=%.3f ms | cta0: scan %.3f ms, sync1 %.3f ms, process %.3f ms, sync2 %.3f ms | batches %llu overflow %llu slices %llu\n",
-                n, fin.levels, fin.rounds, fin.subrounds, grid, g->st.ms_peel_kernel, fin.prof_ns[0] * 1e-6, fin.prof_ns[1] * 1e-6,
-                fin.prof_ns[2] * 1e-6, fin.prof_ns[3] * 1e-6, fin.batches, fin.overflowed, fin.sliced);
+        fprintf(stderr, "[kombgpu] peel n=%u levels=%u rounds=%u grid=%d kernel=%.3f ms | cta0: scan %.3f ms, sync1 %.3f ms, process %.3f ms, sync2 %.3f ms | batches %llu shared %llu slices %llu\n",
+                n, fin.levels, fin.rounds, grid, g->st.ms_peel_kernel, fin.prof_ns[0] * 1e-6, fin.prof_ns[1] * 1e-6,
+                fin.prof_ns[2] * 1e-6, fin.prof_ns[3] * 1e-6, fin.batches, fin.shared, fin.sliced);
     if (trace_path) {
         const uint32_t rows = fin.rounds < trace_cap ? fin.rounds : trace_cap;
         std::vector<unsigned long long> h(6ull * rows);
@@ -214,7 +204,7 @@ int peel_coreness(kombgpu_graph *g) {
     if (fin.n_removed != n) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel ended with %llu of %u vertices peeled", fin.n_removed, n);
     g->st.max_coreness = fin.max_core;
     g->st.peel_levels = fin.levels;
-    g->st.peel_rounds = fin.rounds + fin.subrounds;
+    g->st.peel_rounds = fin.rounds;
     g->has_core = true;
     return KOMBGPU_OK;
 }
