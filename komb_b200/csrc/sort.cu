@@ -1,7 +1,9 @@
 // sort.cu — stable LSD radix sort of 64-bit keys (hits, unitig pairs, CORE-A
 // rank keys).  Integer, HBM-bound: per pass the keys are read twice (digit
 // histogram, scatter) and written once; the scatter stages a tile in shared
-// memory in digit order so global stores are contiguous runs.
+// memory in digit order so global stores are contiguous runs.  A single-read
+// "onesweep" variant (decoupled look-back) was measured and was not faster here:
+// with ~300 tiles in flight the look-back chains cost what the histogram pass costs.
 #include "primitives.cuh"
 
 namespace kg {
@@ -72,17 +74,27 @@ __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(const uint64_
     }
     __syncthreads();
 
+    // rank inside the warp.  Lanes with the same digit are found with one ballot per digit bit
+    // (__match_any_sync does it in one instruction, but MATCH runs on the ADU pipe at a few instructions per
+    // hundred cycles and made this kernel ADU-bound: profiles/r1g).  The group's leader takes the digit's running
+    // count with a shared-memory atomic; a warp issues those in j order, so earlier items get smaller bases and
+    // the sort stays stable without a warp-sync chain.
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         const bool valid = e < tile_count;
-        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : kRadix;  // invalid lanes form their own group
-        const uint32_t same = __match_any_sync(kFullMask, d);
-        const uint32_t before = valid ? s.warp_cnt[warp][d] : 0;
-        rank[j] = before + __popc(same & lanemask_lt());
-        __syncwarp();
-        if (valid && (same & lanemask_lt()) == 0) s.warp_cnt[warp][d] = before + __popc(same);
-        __syncwarp();
+        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : 0u;
+        uint32_t same = __ballot_sync(kFullMask, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if ((mask >> b) == 0) break;  // uniform: digits narrower than 8 bits need fewer ballots
+            const uint32_t vote = __ballot_sync(kFullMask, (d >> b) & 1u);
+            same &= ((d >> b) & 1u) ? vote : ~vote;
+        }
+        const uint32_t lead = valid ? (uint32_t)__ffs(same) - 1u : lane;
+        uint32_t base = 0;
+        if (valid && lead == lane) base = atomicAdd(&s.warp_cnt[warp][d], (uint32_t)__popc(same));
+        rank[j] = __popc(same & lanemask_lt()) + __shfl_sync(kFullMask, base, lead);
     }
     __syncthreads();
 
