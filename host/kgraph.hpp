@@ -39,6 +39,30 @@ inline double seconds_since(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() / 1000000.0;
 }
 
+// Page-locked host array for the large result buffers (DMA at full PCIe rate).
+template <typename T>
+class PinnedArray {
+    kombgpu_ctx *ctx_;
+    T *p_ = nullptr;
+    size_t n_ = 0;
+
+   public:
+    PinnedArray(kombgpu_ctx *ctx, size_t n) : ctx_(ctx), n_(n) {
+        void *q = nullptr;
+        if (kombgpu_pinned_alloc(ctx, (uint64_t)(n ? n : 1) * sizeof(T), &q) != KOMBGPU_OK) {
+            std::cerr << "komb2: " << kombgpu_last_error(ctx) << std::endl;
+            exit(EXIT_FAILURE);
+        }
+        p_ = static_cast<T *>(q);
+    }
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    ~PinnedArray() { kombgpu_pinned_free(ctx_, p_); }
+    T *data() { return p_; }
+    T &operator[](size_t i) { return p_[i]; }
+    size_t size() const { return n_; }
+};
+
 // ---- fast text formatting ------------------------------------------------------
 inline char *put_u64(char *p, uint64_t v) {
     char tmp[24];
@@ -154,7 +178,7 @@ class Kgraph {
         uint32_t n = 0;
         uint64_t m = 0;
         kombgpu_graph_counts(_graph, &n, &m);
-        std::vector<uint32_t> u(m), v(m);
+        PinnedArray<uint32_t> u(_ctx, m), v(_ctx, m);
         int rc = kombgpu_graph_edges(_graph, u.data(), v.data());
         if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_edges", rc);
         write_rows(ef, m, 24, (int)_threads, [&](char *p, size_t i) {
@@ -180,7 +204,7 @@ class Kgraph {
     void runCore(const std::string &dir, HitTable &hits) {
         const std::string kcore_file = dir + "/kcore.tsv";
         const uint32_t n = (uint32_t)hits.names.size();
-        std::vector<int32_t> deg(n), core(n);
+        PinnedArray<int32_t> deg(_ctx, n), core(_ctx, n);
         int rc = kombgpu_degree(_graph, deg.data());
         if (rc != KOMBGPU_OK) gpuError("kombgpu_degree", rc);
         rc = kombgpu_coreness(_graph, core.data());
@@ -202,7 +226,7 @@ class Kgraph {
 
     void anomalyDetection(const std::string &dir, bool weight) {
         const uint32_t n = [&] { uint32_t nn = 0; kombgpu_graph_counts(_graph, &nn, nullptr); return nn; }();
-        std::vector<double> score(n);
+        PinnedArray<double> score(_ctx, n);
         int rc = kombgpu_graph_corea(_graph, _key_mode, score.data());
         if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_corea", rc);
         int32_t max_core = 0;
