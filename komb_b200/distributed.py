@@ -108,13 +108,15 @@ class Comm:
             return arr
         if self.mode == "nccl":
             import torch
-            sizes = self.all_gather_ints([arr.numel()])[:, 0]
-            m = int(sizes.max())
-            pad = torch.zeros(m, dtype=arr.dtype, device=arr.device)
-            pad[:arr.numel()] = arr
-            out = torch.empty(self.world * m, dtype=arr.dtype, device=arr.device)
-            self.dist.all_gather_into_tensor(out, pad)
-            return torch.cat([out[j * m:j * m + int(sizes[j])] for j in range(self.world)])
+            sizes = [int(x) for x in self.all_gather_ints([arr.numel()])[:, 0]]
+            out = torch.empty(sum(sizes), dtype=arr.dtype, device=arr.device)
+            if len(set(sizes)) == 1:
+                self.dist.all_gather_into_tensor(out, arr.contiguous())
+            else:
+                # uneven segments: every rank's piece lands at its final offset, no padding and no second copy
+                offs = np.concatenate([[0], np.cumsum(sizes)])
+                self.dist.all_gather([out[int(offs[j]):int(offs[j + 1])] for j in range(self.world)], arr.contiguous())
+            return out
         host, back = _to_host(arr)
         got = [None] * self.world
         self.dist.all_gather_object(got, host)
