@@ -226,13 +226,11 @@ def run_ours(args):
         """The call a user of the C ABI makes: host hits in (page-locked), every output the
         komb2 host writes to its three files back on the host (page-locked)."""
         g = ctx.build_graph(rk_h.numpy().view(np.uint32), ut_h.numpy().view(np.uint32), N_UNITIGS)
-        core = g.coreness(out=pin["core"])
-        score = g.corea(komb_b200.KEY_REF32, out=pin["score"])
-        deg = g.degree(out=pin["deg"])
-        u, v = g.edges(out=(pin["u"], pin["v"]))
+        r = g.results(komb_b200.KEY_REF32, out={"u": pin["u"], "v": pin["v"], "degree": pin["deg"], "coreness": pin["core"],
+                                                "score": pin["score"]})
         st = g.stats()
         g.close()
-        return st, (u.nbytes + v.nbytes + core.nbytes + deg.nbytes + score.nbytes)
+        return st, sum(a.nbytes for a in r.values())
 
     n_warm = 1 if args.profile else max(args.warmup, 3)
     for _ in range(n_warm):

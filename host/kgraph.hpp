@@ -9,8 +9,8 @@
 //   generateGraph      :287-393               kombgpu_build_graph (pairs, dedup, CSR)
 //   readEdgeList       :395-453               writes edgelist.txt (simple edges, quirk Q7), prints
 //                                             GraphInfo, calls runCore
-//   runCore            :455-484               kombgpu_degree / kombgpu_coreness -> kcore.tsv
-//   anomalyDetection   :637-648               kombgpu_graph_corea -> CoreA_anomaly.txt
+//   runCore            :455-484               degree / coreness (kombgpu_graph_results) -> kcore.tsv
+//   anomalyDetection   :637-648               CORE-A scores (kombgpu_graph_results) -> CoreA_anomaly.txt
 //                       (CombineCoreA::run, src/CombineCoreA.h:16-43)
 // Errors follow the reference: a message on stderr and exit(EXIT_FAILURE)
 // (src/graph.cpp:58-61).
@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -100,6 +101,10 @@ class Kgraph {
     kombgpu_ctx *_ctx = nullptr;
     kombgpu_graph *_graph = nullptr;
     int _key_mode = KOMBGPU_KEY_REF32;
+    // results of the whole path, fetched in one overlapped call (kombgpu_graph_results) by readEdgeList
+    std::unique_ptr<PinnedArray<uint32_t>> _eu, _ev;
+    std::unique_ptr<PinnedArray<int32_t>> _deg, _core;
+    std::unique_ptr<PinnedArray<double>> _score;
 
     [[noreturn]] void fileNotFoundError(const std::string &path) {
         std::cerr << "File " << path << " could not be opened. Exiting..." << std::endl;
@@ -121,6 +126,7 @@ class Kgraph {
         (void)_readlength;  // stored and never read, like the reference (src/graph.cpp:55)
     }
     ~Kgraph() {
+        _eu.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();  // pinned buffers go before the context
         if (_graph) kombgpu_graph_destroy(_graph);
         if (_ctx) kombgpu_ctx_destroy(_ctx);
     }
@@ -178,9 +184,15 @@ class Kgraph {
         uint32_t n = 0;
         uint64_t m = 0;
         kombgpu_graph_counts(_graph, &n, &m);
-        PinnedArray<uint32_t> u(_ctx, m), v(_ctx, m);
-        int rc = kombgpu_graph_edges(_graph, u.data(), v.data());
-        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_edges", rc);
+        // one call fetches everything the three output files need; the edge-list download overlaps the peel
+        _eu.reset(new PinnedArray<uint32_t>(_ctx, m));
+        _ev.reset(new PinnedArray<uint32_t>(_ctx, m));
+        _deg.reset(new PinnedArray<int32_t>(_ctx, n));
+        _core.reset(new PinnedArray<int32_t>(_ctx, n));
+        _score.reset(new PinnedArray<double>(_ctx, n));
+        int rc = kombgpu_graph_results(_graph, _key_mode, _eu->data(), _ev->data(), _deg->data(), _core->data(), _score->data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_results", rc);
+        PinnedArray<uint32_t> &u = *_eu, &v = *_ev;
         write_rows(ef, m, 24, (int)_threads, [&](char *p, size_t i) {
             p = put_u64(p, u[i]); *p++ = '\t';
             p = put_u64(p, v[i]); *p++ = '\n';
@@ -204,11 +216,7 @@ class Kgraph {
     void runCore(const std::string &dir, HitTable &hits) {
         const std::string kcore_file = dir + "/kcore.tsv";
         const uint32_t n = (uint32_t)hits.names.size();
-        PinnedArray<int32_t> deg(_ctx, n), core(_ctx, n);
-        int rc = kombgpu_degree(_graph, deg.data());
-        if (rc != KOMBGPU_OK) gpuError("kombgpu_degree", rc);
-        rc = kombgpu_coreness(_graph, core.data());
-        if (rc != KOMBGPU_OK) gpuError("kombgpu_coreness", rc);
+        PinnedArray<int32_t> &deg = *_deg, &core = *_core;  // fetched by readEdgeList
         FILE *kcf = fopen(kcore_file.c_str(), "w+");
         if (kcf == nullptr) fileNotFoundError(kcore_file);
         fprintf(kcf, "#VID\tName\tCoreness\tDegree\n");
@@ -226,9 +234,7 @@ class Kgraph {
 
     void anomalyDetection(const std::string &dir, bool weight) {
         const uint32_t n = [&] { uint32_t nn = 0; kombgpu_graph_counts(_graph, &nn, nullptr); return nn; }();
-        PinnedArray<double> score(_ctx, n);
-        int rc = kombgpu_graph_corea(_graph, _key_mode, score.data());
-        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_corea", rc);
+        PinnedArray<double> &score = *_score;  // fetched by readEdgeList
         int32_t max_core = 0;
         double max_score = 0.0;
         kombgpu_graph_summary(_graph, &max_core, &max_score);
@@ -246,6 +252,7 @@ class Kgraph {
             });
             fclose(fp);
         }
+        _eu.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();
         kombgpu_graph_destroy(_graph);
         _graph = nullptr;
     }

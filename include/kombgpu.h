@@ -173,6 +173,15 @@ int kombgpu_graph_summary(const kombgpu_graph *g, int32_t *max_coreness, double 
  * device; the three getters above then only copy. */
 int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode);
 
+/* Everything the komb2 host writes to its three files, in one call: runs the peel and
+ * CORE-A if they have not run yet and copies the canonical edge list (u, v: n_edges
+ * entries each), degree, coreness and score (n_vertices entries each) to the host.
+ * The edge list (most of the bytes) is downloaded on a copy stream WHILE the peel
+ * runs; with page-locked buffers (kombgpu_pinned_alloc) that copy is free.
+ * Any output pointer may be NULL (u and v only together). */
+int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t *v, int32_t *degree,
+                          int32_t *coreness, double *score);
+
 int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out);
 
 /* Device pointers of the graph's arrays (valid until kombgpu_graph_destroy);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "kombgpu_graph_corea": (c_int, [c_void_p, c_int, c_void_p]),
     "kombgpu_graph_summary": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_double)]),
     "kombgpu_graph_analyse": (c_int, [c_void_p, c_int]),
+    "kombgpu_graph_results": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kombgpu_graph_stats": (c_int, [c_void_p, POINTER(Stats)]),
     "kombgpu_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
     # multi-GPU partition interface

@@ -212,6 +212,19 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_corea(self._h, int(key_mode), _ptr(s)))
         return s
 
+    def results(self, key_mode: int = KEY_REF32, out: dict | None = None) -> dict:
+        """Everything the komb2 host writes, in one call (kombgpu_graph_results): runs peel + CORE-A if needed;
+        the edge-list download overlaps the peel.  `out` may hold caller buffers under the keys
+        u, v, degree, coreness, score (e.g. Context.pinned_empty arrays)."""
+        n, m = self.counts()
+        out = out or {}
+        r = {"u": self._out(out.get("u"), m, np.uint32), "v": self._out(out.get("v"), m, np.uint32),
+             "degree": self._out(out.get("degree"), n, np.int32), "coreness": self._out(out.get("coreness"), n, np.int32),
+             "score": self._out(out.get("score"), n, np.float64)}
+        self._ctx._check(self._lib.kombgpu_graph_results(self._h, int(key_mode), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["degree"]),
+                                                         _ptr(r["coreness"]), _ptr(r["score"])))
+        return r
+
     def analyse(self, key_mode: int = KEY_REF32):
         self._ctx._check(self._lib.kombgpu_graph_analyse(self._h, int(key_mode)))
 

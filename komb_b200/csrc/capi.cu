@@ -200,6 +200,11 @@ int kombgpu_ctx_create(int device, kombgpu_ctx **out) {
         return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaStreamCreate failed");
     }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaStreamCreate failed");
+    }
     ctx->pinned_bytes = 4096;
     if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
         ctx->pinned = nullptr;
@@ -216,6 +221,7 @@ void kombgpu_ctx_destroy(kombgpu_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->arena) cudaFree(b.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -411,6 +417,42 @@ int kombgpu_graph_summary(const kombgpu_graph *g, int32_t *max_coreness, double 
 int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode) {
     KG_TRY(kombgpu_coreness(g, nullptr));
     return kombgpu_graph_corea(g, key_mode, nullptr);
+}
+
+int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t *v, int32_t *degree, int32_t *coreness,
+                          double *score) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if ((u == nullptr) != (v == nullptr)) return ctx_fail(ctx, KOMBGPU_EINVAL, "u and v must be given together");
+    if (u && g->n_edges && !g->edges) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no canonical edge list");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t E = g->n_edges;
+    const uint32_t n = g->n;
+    DevBuf<uint32_t> du, dv;  // live until the copy stream has drained
+    cudaEvent_t ready = nullptr;
+    // 1. edge list + degree: final after the build -> start their download on the copy stream
+    if (u && E) {
+        KG_ALLOC(ctx, du, E);
+        KG_ALLOC(ctx, dv, E);
+        KG_LAUNCH(ctx, unpack_edges_kernel, min(ceil_div_u64(E, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->edges, E, du.p, dv.p);
+    }
+    KG_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ready, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
+    if (e == cudaSuccess && u && E) e = cudaMemcpyAsync(u, du.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess && v && E) e = cudaMemcpyAsync(v, dv.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess && degree && n) e = cudaMemcpyAsync(degree, g->deg, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    cudaEventDestroy(ready);
+    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); return ctx_fail(ctx, KOMBGPU_ECUDA, "results: %s", cudaGetErrorString(e)); }
+    // 2. peel + CORE-A on the compute stream meanwhile
+    int rc = kombgpu_coreness(g, nullptr);
+    if (rc == KOMBGPU_OK && (score || !g->has_score)) rc = kombgpu_graph_corea(g, key_mode, nullptr);
+    if (rc == KOMBGPU_OK && coreness && n) rc = download(ctx, g->core, coreness, n);
+    if (rc == KOMBGPU_OK && score && n) rc = download(ctx, g->score, score, n);
+    cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+    if (rc != KOMBGPU_OK) return rc;
+    if (ce != cudaSuccess) return ctx_fail(ctx, KOMBGPU_ECUDA, "results copy stream: %s", cudaGetErrorString(ce));
+    return KOMBGPU_OK;
 }
 
 int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out) {

@@ -33,6 +33,7 @@ struct kombgpu_ctx {
     size_t l2_bytes = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // downloads that overlap compute (kombgpu_graph_results)
     std::string err;
     std::vector<kg::ArenaBlock> arena;  // cached device workspace, reused across calls
     uint64_t launches = 0;              // kernels launched through this context

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kPeelThreads) part_scan_kernel(int32_t k, cons
                                                                  uint32_t *alive_dst, const int32_t *deg, uint64_t *Q,
                                                                  PeelState *st) {
     __shared__ BlockShared sh;
-    int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, Q, &st->q_tail, &st->front_cnt[0], &st->alive_out[0], sh);
+    int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, Q, &st->q_tail, &st->front_cnt[0], &st->alive_out[0], &st->n_isolated, sh);
     local_min = warp_reduce_min(local_min);
     if (lane_id() == 0 && local_min != INT32_MAX) atomicMin(&st->next_min[0], local_min);
 }

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         const bool prof = (blockIdx.x == 0 && tid == 0);
         unsigned long long tp0 = prof ? global_ns() : 0;
         int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, Q, &st->q_tail, &st->front_cnt[par],
-                                       &st->alive_out[par], sh);
+                                       &st->alive_out[par], &st->n_isolated, sh);
         local_min = warp_reduce_min(local_min);
         if (lane == 0 && local_min != INT32_MAX) atomicMin(&st->next_min[par], local_min);
         unsigned long long tp1 = prof ? global_ns() : 0;
@@ -201,9 +201,10 @@ int peel_coreness(kombgpu_graph *g) {
         }
     }
     if (fin.error) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel invariant broken (code %u, %llu of %u vertices peeled)", fin.error, fin.n_removed, n);
-    if (fin.n_removed != n) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel ended with %llu of %u vertices peeled", fin.n_removed, n);
+    if (fin.n_removed + fin.n_isolated != n)
+        return ctx_fail(ctx, KOMBGPU_EINTERNAL, "peel ended with %llu of %u vertices peeled", fin.n_removed + fin.n_isolated, n);
     g->st.max_coreness = fin.max_core;
-    g->st.peel_levels = fin.levels;
+    g->st.peel_levels = fin.levels + (fin.n_isolated ? 1u : 0u);  // level 0 is handled by the scan alone
     g->st.peel_rounds = fin.rounds;
     g->has_core = true;
     return KOMBGPU_OK;

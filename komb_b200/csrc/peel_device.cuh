@@ -55,7 +55,8 @@ struct PeelState {
     uint32_t levels;        // non-empty levels
     uint32_t rounds;        // scan phases executed
     int32_t max_core;
-    unsigned long long n_removed;  // vertices peeled (must end at n)
+    unsigned long long n_removed;  // vertices peeled through the pool
+    unsigned long long n_isolated; // degree-0 vertices, peeled by the level-0 scan itself (n_removed + n_isolated must end at n)
     unsigned long long shared;     // discoveries handed to other CTAs through the pool
     unsigned long long sliced;     // slices published
     // CTA 0's view of where the time goes (ns): scan, barrier after scan, process, barrier after process
@@ -113,9 +114,11 @@ struct PartView {
 // atomics in all.  Returns the thread's minimum survivor degree.
 __device__ __forceinline__ int32_t scan_alive(const int32_t k, const uint32_t *alive_src, const uint32_t n_alive,
                                               uint32_t *alive_dst, const int32_t *deg, uint64_t *Q, uint32_t *q_tail,
-                                              uint32_t *front_cnt, uint32_t *alive_out, BlockShared &sh) {
+                                              uint32_t *front_cnt, uint32_t *alive_out, unsigned long long *n_isolated,
+                                              BlockShared &sh) {
     const uint32_t tid = threadIdx.x;
     int32_t local_min = INT32_MAX;
+    uint32_t isolated = 0;
     for (uint64_t tile = (uint64_t)blockIdx.x * kScanTileV; tile < n_alive; tile += (uint64_t)gridDim.x * kScanTileV) {
         uint32_t v[kScanItems];
         uint32_t flag[kScanItems];  // 1 = frontier, 0x10000 = survivor
@@ -132,7 +135,7 @@ __device__ __forceinline__ int32_t scan_alive(const int32_t k, const uint32_t *a
             const uint64_t i = tile + (uint64_t)j * kPeelThreads + tid;
             if (i < n_alive) {
                 const int32_t d = __ldcg(&deg[v[j]]);
-                if (d == k) flag[j] = 1u;
+                if (d == k) { if (k > 0) flag[j] = 1u; else ++isolated; }  // a degree-0 vertex has no row to walk: peeled right here
                 else if (d > k) { flag[j] = 0x10000u; local_min = min(local_min, d); }
             }
             mine += flag[j];
@@ -153,6 +156,10 @@ __device__ __forceinline__ int32_t scan_alive(const int32_t k, const uint32_t *a
             else if (flag[j]) alive_dst[spos++] = v[j];
         }
         __syncthreads();  // tile_base is reused by the next tile
+    }
+    if (k == 0) {
+        isolated = warp_reduce_add(isolated);
+        if (lane_id() == 0 && isolated) atomicAdd(n_isolated, (unsigned long long)isolated);
     }
     return local_min;
 }

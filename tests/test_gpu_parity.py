@@ -197,3 +197,25 @@ def test_pinned_out_buffers(ctx, oracle_mod):
         assert s.shape == (3000,) and np.all(s >= 0)
         with pytest.raises(ValueError):
             g.degree(out=np.empty(10, np.int32))
+
+
+def test_results_one_call(ctx, oracle_mod):
+    """kombgpu_graph_results: everything the host writes, edge download overlapped with the peel."""
+    m1, m2 = synth.metagenome_hits(30000, 90000, seed=8)
+    rk = np.concatenate([m1.read_key, m2.read_key]); ut = np.concatenate([m1.unitig, m2.unitig])
+    exp_edges, _, _ = oracle_mod.build_edges(rk, ut)
+    exp_deg, exp_core = oracle_mod.coreness(30000, exp_edges)
+    out = {"u": ctx.pinned_empty(exp_edges.shape[0] + 10, np.uint32), "v": ctx.pinned_empty(exp_edges.shape[0] + 10, np.uint32)}
+    with ctx.build_graph(rk, ut, 30000) as g:
+        r = g.results(out=out)
+        assert np.array_equal(oracle_mod.pack_edges(r["u"], r["v"]), exp_edges)
+        assert np.array_equal(r["degree"], exp_deg) and np.array_equal(r["coreness"], exp_core)
+        np.testing.assert_allclose(r["score"], oracle_mod.corea(exp_core, exp_deg, oracle_mod.KEY_REF32), rtol=RTOL, atol=ATOL)
+        r2 = g.results(komb_b200_key_exact())       # second call: nothing is recomputed except CORE-A in the other key mode
+        assert np.array_equal(r2["coreness"], exp_core)
+        np.testing.assert_allclose(r2["score"], oracle_mod.corea(exp_core, exp_deg, oracle_mod.KEY_EXACT64), rtol=RTOL, atol=ATOL)
+
+
+def komb_b200_key_exact():
+    import komb_b200
+    return komb_b200.KEY_EXACT64
