@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "peel_device.cuh"
+#include "peel_warp.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -37,12 +38,19 @@ namespace {
 
 using namespace peel;
 
+union PeelShared {
+    BlockShared cta;   // scan phase (both modes) and the CTA-wide process phase
+    WarpShared warp;   // warp-autonomous process phase (the phases are separated by grid barriers)
+};
+
+template <bool kWarpMode>
 __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const uint64_t *__restrict__ row_ptr,
                                                             const uint32_t *__restrict__ col, int32_t *deg,
                                                             uint64_t *Q, uint32_t cap, uint32_t *alive_a, uint32_t *alive_b,
                                                             PeelState *st) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ BlockShared sh;
+    __shared__ PeelShared shu;
+    BlockShared &sh = shu.cta;
     const uint32_t tid = threadIdx.x, lane = lane_id();
 
     int32_t k = 0;
@@ -98,7 +106,8 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         }
 
         // ---------------- PROCESS ----------------
-        removed += process_level<false>(k, round, Q, cap, row_ptr, col, deg, st, sh, PartView{});
+        if (kWarpMode) removed += process_level_warp<false>(k, round, Q, cap, row_ptr, col, deg, st, shu.warp, PartView{});
+        else removed += process_level<false>(k, round, Q, cap, row_ptr, col, deg, st, sh, PartView{});
         unsigned long long tp3 = prof ? global_ns() : 0;
         grid.sync();
         if (prof) {
@@ -129,8 +138,12 @@ int peel_coreness(kombgpu_graph *g) {
     if (n == 0) { g->has_core = true; return KOMBGPU_OK; }
     KG_CUDA(ctx, cudaMemcpyAsync(g->core, g->deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
 
+    const char *mode_env = getenv("KOMBGPU_PEEL_MODE");   // "cta": the CTA-wide process phase (kept for A/B measurements)
+    const bool warp_mode = !(mode_env && mode_env[0] == 'c');
+    void *kernel = warp_mode ? (void *)peel_kernel<true> : (void *)peel_kernel<false>;
     int per_sm = 0;
-    KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel, kPeelThreads, 0));
+    if (warp_mode) KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<true>, kPeelThreads, 0));
+    else KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<false>, kPeelThreads, 0));
     if (per_sm < 1) return ctx_fail(ctx, KOMBGPU_ECUDA, "peel kernel does not fit on an SM");
     const int grid = per_sm * ctx->sm_count;  // persistent: every CTA resident (cooperative launch)
 
@@ -139,8 +152,10 @@ int peel_coreness(kombgpu_graph *g) {
     DevBuf<PeelState> state(ctx, 1);
     // every vertex enters the pool at most once; a row is sliced at most once (<= 2E/kSplit long rows, each giving
     // <= len/kSliceLen + 1 slices); plus the slots idle CTAs reserve past the tail
-    const uint64_t cap64 = (uint64_t)n + 2 * g->n_edges / kSliceLen + 2 * g->n_edges / kSplit + (uint64_t)grid * kClaimMax + 64;
-    if (cap64 >= 0xffffffffull || 2 * g->n_edges >= (1ull << (63 - kSliceLenBits)))
+    // (warp mode re-queues the pieces of rows longer than kWarpSplit, through the pool when the CTA's ring is busy)
+    const uint64_t cap64 = (uint64_t)n + 2 * g->n_edges / kSliceLen + 2 * g->n_edges / kSplit + 4 * g->n_edges / kWarpSplitMin +
+                           (uint64_t)grid * kClaimMax + 64;
+    if (cap64 >= 0xffffffffull || 2 * g->n_edges >= (1ull << (62 - kSliceLenBits)))
         return ctx_fail(ctx, KOMBGPU_EINVAL, "graph too large for the pool encoding");
     const uint32_t cap = (uint32_t)cap64;
     KG_ALLOC(ctx, pool, cap);
@@ -150,6 +165,12 @@ int peel_coreness(kombgpu_graph *g) {
     if (!state) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
     PeelState init{};
     for (int i = 0; i < 3; ++i) init.next_min[i] = INT32_MAX;
+    init.tune[0] = (uint32_t)kRingKeep;
+    init.tune[1] = kWarpSplit;
+    init.tune[2] = 0;
+    if (const char *e = getenv("KOMBGPU_PEEL_KEEP")) init.tune[0] = (uint32_t)atoi(e);
+    if (const char *e = getenv("KOMBGPU_PEEL_WSPLIT")) init.tune[1] = (uint32_t)atoi(e) < kWarpSplitMin ? kWarpSplitMin : (uint32_t)atoi(e);
+    if (const char *e = getenv("KOMBGPU_PEEL_PARK")) init.tune[2] = (uint32_t)atoi(e);
     DevBuf<unsigned long long> trace;
     const char *trace_path = getenv("KOMBGPU_TRACE");
     const uint32_t trace_cap = 1u << 16;
@@ -174,7 +195,7 @@ int peel_coreness(kombgpu_graph *g) {
     KG_CUDA(ctx, cudaEventCreate(&ev0));
     KG_CUDA(ctx, cudaEventCreate(&ev1));
     KG_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
-    cudaError_t le = cudaLaunchCooperativeKernel((void *)peel_kernel, dim3(grid), dim3(kPeelThreads), args, 0, ctx->stream);
+    cudaError_t le = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kPeelThreads), args, 0, ctx->stream);
     cudaEventRecord(ev1, ctx->stream);
     ctx->launches++;
     if (le == cudaSuccess) le = cudaEventSynchronize(ev1);

@@ -1,0 +1,456 @@
+// peel_warp.cuh — PROCESS phase of one peel level with warp-autonomous workers.
+//
+// The CTA-wide version in peel_device.cuh moves a whole CTA through every cascade step (block scan, five CTA
+// barriers per batch: ~3.6 us per dependent step measured on B200).  Here the 16 warps of a CTA never meet at a
+// barrier inside a level.  They share one shared-memory TICKET RING:
+//
+//   r_tail  tickets pushed (slot written right after the fetch-add that reserves it)
+//   r_head  tickets claimed or reserved by consumers
+//   r_done  tickets fully processed, credited after the consumer's own pushes
+//
+// A warp claims tickets with one shared-memory fetch-add; if the ring is empty the claim is a reservation and the
+// warp polls the slot's own word, so the warp that discovers the next vertex hands it over with one store.  A
+// cascade step is  atomicSub -> ballot -> ring store -> (any parked warp) -> row_ptr -> col -> atomicSub  with no
+// barrier and no block-wide scan.  Edges of a batch (up to 32 rows, one per lane) are spread over the lanes with a
+// shuffle-based search of the row prefix, four independent chains per lane.
+//
+// The global pool protocol of peel_device.cuh is unchanged, but it is spoken by ONE warp per CTA at a time, the
+// AGENT: the parked warp that owns the ticket r_tail (the slot the next push will fill).  When the CTA is locally
+// quiescent (r_done == r_tail) the agent settles the CTA's credit with q_done, detects the end of the level, or
+// claims / reserves pool slots.  Pool entries known to be below q_tail are handed to the workers as RANGE
+// descriptors (one ring ticket = up to 32 pool entries, loaded by the worker itself), reserved pool slots are
+// polled by the agent and copied into the ring when they are written.  Discoveries beyond what the CTA's warps can
+// start on at once (kRingKeep queued tickets) go to the pool, where idle CTAs' agents are parked.
+#pragma once
+
+#include "peel_device.cuh"
+
+namespace kg {
+namespace peel {
+
+constexpr int kRing = 4096;               // ring slots (power of two)
+constexpr uint32_t kRingMask = kRing - 1;
+constexpr int32_t kRingKeep = 16;         // default of WarpTune::keep
+constexpr uint64_t kRangeBit = 1ull << 62;  // ring-only entry: kRangeBit | first_pool_slot << 8 | count
+constexpr uint32_t kRangeLen = 32;
+constexpr uint32_t kWarpSplit = 256;       // default of WarpTune::wsplit
+constexpr uint32_t kWarpSplitMin = 128;    // lower bound of the knob (sizes the pool)
+constexpr uint32_t kSpinCheck = 1u << 16;  // polls between two looks at the watchdog clock
+
+// run-time knobs (PeelState::tune; defaults below, overridable through KOMBGPU_PEEL_* for measurements)
+struct WarpTune {
+    int32_t keep;      // queued ring tickets above which discoveries are shared through the pool
+    uint32_t wsplit;   // edges of a row one warp keeps
+    uint32_t park_ns;  // sleep between two polls of a parked warp (0 = spin)
+};
+
+struct WarpShared {
+    uint64_t ring[kRing];
+    uint32_t r_head, r_tail, r_done;
+    uint32_t over;        // the level has ended (or an invariant broke): every warp leaves
+    uint32_t lock;        // agent mutual exclusion
+    uint32_t credit;      // pool tasks this CTA took and has not credited to q_done yet
+    uint32_t gb, ge;      // reserved pool slots [gb, ge) this CTA polls
+    uint32_t polls;
+    uint32_t removed;
+    uint32_t shared_cnt;
+    uint32_t batches;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ uint64_t lds_u64(const uint64_t *p) { return *reinterpret_cast<const volatile uint64_t *>(p); }
+__device__ __forceinline__ void sts_u32(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+__device__ __forceinline__ void sts_u64(uint64_t *p, uint64_t v) { *reinterpret_cast<volatile uint64_t *>(p) = v; }
+
+// store one ring ticket; the slot's previous lap has been consumed long ago (the ring never holds more than
+// kRingKeep + 16 warps x 128 tickets), the wait only makes that explicit
+__device__ __forceinline__ void ring_put(WarpShared &sh, uint32_t ticket, uint64_t e) {
+    uint64_t *slot = &sh.ring[ticket & kRingMask];
+    uint32_t tries = 0;
+    while (lds_u64(slot) != kEmpty && ++tries < (1u << 24)) {}
+    sts_u64(slot, e);
+}
+
+// One batch of a warp: lane i holds task `ent` (a vertex, a slice of a hub row, or kEmpty).  Returns how many
+// vertices were peeled.
+template <bool kDist>
+__device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t k, const uint64_t *__restrict__ row_ptr,
+                                               const uint32_t *__restrict__ col, int32_t *deg, uint64_t *Q, const uint32_t cap,
+                                               PeelState *st, WarpShared &sh, const PartView &part, const WarpTune &tn,
+                                               uint32_t &n_shared) {
+    const uint32_t lane = lane_id();
+    uint32_t my_len = 0;
+    uint64_t my_row = 0;
+    bool is_vertex = false;
+    if (ent != kEmpty) {
+        if (ent & kSliceBit) {
+            my_row = (ent & ~kSliceBit) >> kSliceLenBits;
+            my_len = (uint32_t)(ent & ((1u << kSliceLenBits) - 1));
+        } else {
+            const uint32_t v = (uint32_t)ent;
+            is_vertex = true;
+            my_row = row_ptr[v];
+            my_len = (uint32_t)(row_ptr[v + 1] - my_row);
+            if (my_len > kSplit) {
+                // hub row: hand it to the whole grid as slices
+                const uint32_t n_sl = (my_len + kSliceLen - 1) / kSliceLen;
+                const uint32_t s0 = atomicAdd(&st->q_tail, n_sl);
+                for (uint32_t i = 0; i < n_sl; ++i) {
+                    const uint64_t e = kSliceBit | ((my_row + (uint64_t)i * kSliceLen) << kSliceLenBits) |
+                                       min(kSliceLen, my_len - i * kSliceLen);
+                    if (s0 + i < cap) st_volatile_u64(&Q[s0 + i], e);
+                    else atomicExch(&st->error, 3u);
+                }
+                atomicAdd(&st->sliced, (unsigned long long)n_sl);
+                my_len = 0;
+            }
+        }
+    }
+    // rows longer than kWarpSplit: keep the first piece, queue the rest as slices any warp (or, when the ring is
+    // busy, any CTA) can take -- a long row must not serialise on one warp
+    {
+        const uint32_t extra = my_len > tn.wsplit ? (my_len - 1) / tn.wsplit : 0u;
+        if (__ballot_sync(kFullMask, extra != 0)) {
+            const uint32_t xin = warp_incl_scan_add(extra);
+            const uint32_t xtot = __shfl_sync(kFullMask, xin, 31);
+            uint32_t pos = 0, to_pool = 0;
+            if (lane == 0) {
+                const int32_t queued = (int32_t)(lds_u32(&sh.r_tail) - lds_u32(&sh.r_head));
+                to_pool = (queued >= tn.keep || xtot > 128u) ? 1u : 0u;
+                pos = to_pool ? atomicAdd(&st->q_tail, xtot) : atomicAdd(&sh.r_tail, xtot);
+            }
+            pos = __shfl_sync(kFullMask, pos, 0) + (xin - extra);
+            to_pool = __shfl_sync(kFullMask, to_pool, 0);
+            for (uint32_t i = 1; i <= extra; ++i, ++pos) {
+                const uint64_t e = kSliceBit | ((my_row + (uint64_t)i * tn.wsplit) << kSliceLenBits) |
+                                   min(tn.wsplit, my_len - i * tn.wsplit);
+                if (to_pool) {
+                    if (pos < cap) st_volatile_u64(&Q[pos], e);
+                    else atomicExch(&st->error, 3u);
+                } else {
+                    ring_put(sh, pos, e);
+                }
+            }
+            if (extra) my_len = tn.wsplit;
+        }
+    }
+    const uint32_t incl = warp_incl_scan_add(my_len);
+    const uint32_t excl = incl - my_len;
+    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+    const uint32_t row_lo = (uint32_t)my_row, row_hi = (uint32_t)(my_row >> 32);
+    const bool direct = total <= 32u * kUnroll;
+
+    for (uint32_t base = 0; base < total; base += 32u * kUnroll) {
+        uint32_t u[kUnroll];
+        int32_t d[kUnroll];
+        bool push[kUnroll];
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) {
+            const uint32_t e = base + t * 32u + lane;
+            // owner row: the last lane j with excl[j] <= e (rows of length 0 are skipped by "last")
+            uint32_t j = 0;
+#pragma unroll
+            for (uint32_t s = 16; s > 0; s >>= 1) {
+                const uint32_t x = __shfl_sync(kFullMask, excl, (j + s) & 31u);
+                if (x <= e) j += s;
+            }
+            const uint32_t ex_j = __shfl_sync(kFullMask, excl, j);
+            const uint32_t lo = __shfl_sync(kFullMask, row_lo, j), hi = __shfl_sync(kFullMask, row_hi, j);
+            u[t] = kFullMask;
+            if (e < total) u[t] = col[(((uint64_t)hi << 32) | lo) + (e - ex_j)];
+        }
+        if (kDist) {
+            // split off the neighbours other ranks own: ship their ids, keep local ones as local ids
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) {
+                const bool valid = u[t] != kFullMask;
+                const uint32_t loc = u[t] - part.v_lo;
+                const bool remote = valid && loc >= part.n_local;
+                const uint32_t rm = __ballot_sync(kFullMask, remote);
+                if (rm) {
+                    uint32_t pos = 0;
+                    if (lane == 0) pos = atomicAdd(part.outbox_cnt, (uint32_t)__popc(rm));
+                    pos = __shfl_sync(kFullMask, pos, 0) + __popc(rm & lanemask_lt());
+                    if (remote) part.outbox[pos] = u[t];
+                }
+                u[t] = (valid && !remote) ? loc : kFullMask;
+            }
+        }
+        if (direct) {
+            // latency-bound batch (one iteration): the decrement goes out right away and is undone if it lands
+            // at or below k -- one dependent round trip less on the cascade's critical path
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? atomicSub(&deg[u[t]], 1) : INT32_MAX;
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) {
+                push[t] = d[t] == k + 1;
+                if (d[t] <= k) atomicAdd(&deg[u[t]], 1);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? __ldcg(&deg[u[t]]) : INT32_MIN;
+#pragma unroll
+            for (int t = 0; t < kUnroll; ++t) {
+                push[t] = false;
+                if (d[t] > k) {
+                    const int32_t old = atomicSub(&deg[u[t]], 1);
+                    if (old == k + 1) push[t] = true;             // u just reached level k: ours to peel
+                    else if (old <= k) atomicAdd(&deg[u[t]], 1);  // already at level k: undo (clamp)
+                }
+            }
+        }
+        uint32_t c = 0;
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) c += push[t] ? 1u : 0u;
+        if (__ballot_sync(kFullMask, c != 0) == 0) continue;
+        const uint32_t inc = warp_incl_scan_add(c);
+        const uint32_t tot = __shfl_sync(kFullMask, inc, 31);
+        uint32_t pos = 0, to_pool = 0;
+        if (lane == 0) {
+            const int32_t queued = (int32_t)(lds_u32(&sh.r_tail) - lds_u32(&sh.r_head));
+            to_pool = queued >= tn.keep ? 1u : 0u;
+            pos = to_pool ? atomicAdd(&st->q_tail, tot) : atomicAdd(&sh.r_tail, tot);
+        }
+        pos = __shfl_sync(kFullMask, pos, 0) + (inc - c);
+        to_pool = __shfl_sync(kFullMask, to_pool, 0);
+        if (to_pool) n_shared += c;
+#pragma unroll
+        for (int t = 0; t < kUnroll; ++t) {
+            if (!push[t]) continue;
+            if (to_pool) {
+                if (pos < cap) st_volatile_u64(&Q[pos], (uint64_t)u[t]);
+                else atomicExch(&st->error, 3u);
+            } else {
+                ring_put(sh, pos, (uint64_t)u[t]);
+            }
+            ++pos;
+        }
+    }
+    return (uint32_t)__popc(__ballot_sync(kFullMask, is_vertex));
+}
+
+// One step of the agent (whole warp, sh.lock held by lane 0).  Either delivers work into the ring, ends the level
+// (sh.over), or does nothing because other warps of the CTA are still working.
+__device__ __forceinline__ void agent_step(const uint64_t token, uint64_t *Q, const uint32_t cap, PeelState *st, WarpShared &sh,
+                                           unsigned long long &idle_since) {
+    const uint32_t lane = lane_id();
+    const uint32_t gb = lds_u32(&sh.gb), ge = lds_u32(&sh.ge);
+    // 1. reserved pool slots: copy the leading run of written ones into the ring
+    if (gb < ge) {
+        uint64_t e = kEmpty;
+        bool tok = false;
+        if (lane < ge - gb) {
+            e = ld_volatile_u64(&Q[gb + lane]);
+            if (e == token) { tok = true; st_volatile_u64(&Q[gb + lane], kEmpty); }  // leave the slot clean
+        }
+        const uint32_t rm = __ballot_sync(kFullMask, entry_is_task(e));
+        const uint32_t tk = __ballot_sync(kFullMask, tok);
+        const uint32_t m = (rm == kFullMask) ? 32u : (uint32_t)__ffs(~rm) - 1u;
+        if (m) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(&sh.r_tail, m);
+            pos = __shfl_sync(kFullMask, pos, 0);
+            if (lane < m) ring_put(sh, pos + lane, e);
+            if (lane == 0) { sts_u32(&sh.gb, gb + m); sts_u32(&sh.credit, lds_u32(&sh.credit) + m); sts_u32(&sh.polls, 0); }
+            idle_since = 0;
+            return;
+        }
+        if (tk) {  // level over: nothing can be pending anywhere
+            if (lane == 0) sts_u32(&sh.over, 1u);
+            return;
+        }
+    }
+    // 2. anything still running in this CTA?  (r_done is read first: both counters are monotone and
+    //    r_done <= r_tail, so equality of this pair means quiescence at the time r_done was read)
+    uint32_t quiet = 0;
+    if (lane == 0) {
+        const uint32_t dn = lds_u32(&sh.r_done);
+        const uint32_t tl = lds_u32(&sh.r_tail);
+        quiet = dn == tl ? 1u : 0u;
+    }
+    if (!__shfl_sync(kFullMask, quiet, 0)) return;
+    // 3. the CTA is drained: settle its credit, then end the level, keep waiting, or claim / reserve pool slots
+    uint32_t over = 0, fin_tail = 0, fin_head = 0, begin = 0, sure = 0, end = 0;
+    if (lane == 0) {
+        const uint32_t credit = lds_u32(&sh.credit);
+        uint4 a = make_uint4(0, 0, 0, 0);
+        bool have_a = false;
+        if (credit) {
+            __threadfence();
+            const uint32_t old = atomicAdd(&st->q_done, credit);
+            a = ld_volatile_u4(st);  // q_head, q_tail, q_done, error
+            have_a = true;
+            sts_u32(&sh.credit, 0);
+            if (old + credit == a.y) { fin_tail = a.y; fin_head = min(a.x, cap); over = 1; }  // quiescent, final
+        }
+        if (!over) {
+            if (gb < ge) {
+                // parked on reserved slots: only rarely look at the shared counters
+                const uint32_t polls = lds_u32(&sh.polls) + 1;
+                sts_u32(&sh.polls, polls);
+                if (have_a || polls == 1 || (polls & 7u) == 0) {
+                    if (!have_a) a = ld_volatile_u4(st);
+                    if (a.z == a.y || a.w) over = 1;  // q_done == q_tail: final, nobody can append any more
+                    else if (idle_since == 0) idle_since = global_ns();
+                    else if (global_ns() - idle_since > kWatchdogNs) { atomicExch(&st->error, 2u); over = 1; }
+                }
+                if (!over) __nanosleep(100);
+            } else {
+                if (!have_a) a = ld_volatile_u4(st);
+                if (a.z == a.y || a.w) {
+                    over = 1;
+                } else {
+                    uint32_t take = 1;
+                    if (a.x < a.y) take = min(max((a.y - a.x + gridDim.x - 1) / gridDim.x, 1u), kClaimMax);
+                    begin = atomicAdd(&st->q_head, take);
+                    end = min(begin + take, cap);
+                    if (begin >= cap) { atomicExch(&st->error, 4u); over = 1; end = begin; }
+                    sure = min(max(a.y, begin), end);  // slots below the tail seen before the claim: written, or about to be
+                    sts_u32(&sh.polls, 0);
+                }
+            }
+        }
+    }
+    over = __shfl_sync(kFullMask, over, 0);
+    fin_tail = __shfl_sync(kFullMask, fin_tail, 0);
+    fin_head = __shfl_sync(kFullMask, fin_head, 0);
+    begin = __shfl_sync(kFullMask, begin, 0);
+    sure = __shfl_sync(kFullMask, sure, 0);
+    end = __shfl_sync(kFullMask, end, 0);
+    // this CTA ended the level: wake every agent parked on a reserved slot
+    for (uint32_t i = fin_tail + lane; i < fin_head; i += 32) st_volatile_u64(&Q[i], token);
+    if (over) {
+        if (lane == 0) sts_u32(&sh.over, 1u);
+        return;
+    }
+    if (end > begin) {
+        const uint32_t n_desc = (sure - begin + kRangeLen - 1) / kRangeLen;
+        if (n_desc) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(&sh.r_tail, n_desc);
+            pos = __shfl_sync(kFullMask, pos, 0);
+            for (uint32_t i = lane; i < n_desc; i += 32) {
+                const uint32_t s = begin + i * kRangeLen;
+                ring_put(sh, pos + i, kRangeBit | ((uint64_t)s << 8) | (uint64_t)min(kRangeLen, sure - s));
+            }
+        }
+        if (lane == 0) {
+            sts_u32(&sh.credit, lds_u32(&sh.credit) + (sure - begin));
+            sts_u32(&sh.gb, sure);
+            sts_u32(&sh.ge, end);
+        }
+        idle_since = 0;
+    }
+}
+
+// PROCESS phase of one level for one CTA (all kPeelThreads threads call it; returns the vertices the CTA peeled).
+template <bool kDist>
+__device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const uint32_t round, uint64_t *Q, const uint32_t cap,
+                                                       const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                                                       int32_t *deg, PeelState *st, WarpShared &sh, const PartView &part) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
+    const uint64_t token = ((uint64_t)kTokenHi << 32) | round;
+    for (uint32_t i = tid; i < (uint32_t)kRing; i += kPeelThreads) sh.ring[i] = kEmpty;
+    if (tid == 0) {
+        sh.r_head = 0; sh.r_tail = 0; sh.r_done = 0;
+        sh.over = 0; sh.lock = 0; sh.credit = 0; sh.gb = 0; sh.ge = 0; sh.polls = 0;
+        sh.removed = 0; sh.shared_cnt = 0; sh.batches = 0;
+    }
+    __syncthreads();
+
+    WarpTune tn;
+    tn.keep = (int32_t)st->tune[0];
+    tn.wsplit = st->tune[1];
+    tn.park_ns = st->tune[2];
+    uint32_t rb = 0, re = 0;   // ring tickets this warp owns
+    uint32_t removed = 0, n_shared = 0, batches = 0;
+    uint32_t spins = 0;
+    unsigned long long idle_since = 0;  // lane 0
+
+    while (true) {
+        if (rb == re) {
+            if (lane == 0) {
+                const int32_t avail = (int32_t)(lds_u32(&sh.r_tail) - lds_u32(&sh.r_head));
+                const uint32_t take = avail > 0 ? (uint32_t)min(max(avail / (2 * kPeelWarps), 1), 32) : 1u;
+                rb = atomicAdd(&sh.r_head, take);
+                re = rb + take;
+            }
+            rb = __shfl_sync(kFullMask, rb, 0);
+            re = __shfl_sync(kFullMask, re, 0);
+        }
+        // the leading run of written tickets in the owned range
+        uint64_t ent = kEmpty;
+        if (lane < re - rb) ent = lds_u64(&sh.ring[(rb + lane) & kRingMask]);
+        const uint32_t rm = __ballot_sync(kFullMask, ent != kEmpty);
+        uint32_t m = (rm == kFullMask) ? 32u : (uint32_t)__ffs(~rm) - 1u;
+        if (m == 0) {
+            // parked on ticket rb
+            uint32_t act = 0;  // 1: leave, 2: act as the agent
+            if (lane == 0) {
+                if (lds_u32(&sh.over)) act = 1;
+                else if (lds_u32(&sh.r_tail) == rb && atomicCAS(&sh.lock, 0u, 1u) == 0u)
+                    // re-check under the lock: the slot may have been filled, the level may have ended
+                    act = (lds_u32(&sh.r_tail) == rb && !lds_u32(&sh.over)) ? 2u : 3u;
+            }
+            act = __shfl_sync(kFullMask, act, 0);
+            if (act == 1) break;
+            if (act >= 2) {
+                if (act == 2) agent_step(token, Q, cap, st, sh, idle_since);
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); atomicExch(&sh.lock, 0u); }
+            } else {
+                if ((++spins & (kSpinCheck - 1)) == 0 && lane == 0) {
+                    if (idle_since == 0) idle_since = global_ns();
+                    else if (global_ns() - idle_since > kWatchdogNs) { atomicExch(&st->error, 2u); sts_u32(&sh.over, 1u); }
+                }
+                if (tn.park_ns) __nanosleep(tn.park_ns);
+            }
+            continue;
+        }
+        idle_since = 0;
+        // a range descriptor is a batch of its own
+        const uint32_t dm = __ballot_sync(kFullMask, ent != kEmpty && (ent & kSliceBit) == 0 && (ent & kRangeBit) != 0) & ((m == 32u) ? kFullMask : ((1u << m) - 1u));
+        bool is_range = false;
+        if (dm & 1u) { m = 1; is_range = true; }
+        else if (dm) m = (uint32_t)__ffs(dm) - 1u;
+        if (lane < m) sts_u64(&sh.ring[(rb + lane) & kRingMask], kEmpty);  // free the slots for the next lap
+        if (lane >= m) ent = kEmpty;
+        rb += m;
+        if (is_range) {
+            const uint64_t desc = __shfl_sync(kFullMask, ent, 0);
+            const uint32_t s = (uint32_t)(desc >> 8), cnt = (uint32_t)(desc & 0xffu);
+            ent = kEmpty;
+            if (lane < cnt) {
+                uint32_t tries = 0;
+                while (true) {
+                    ent = ld_volatile_u64(&Q[s + lane]);
+                    if (entry_is_task(ent)) break;
+                    if ((++tries & (kSpinCheck - 1)) == 0 && __ldcg(&st->error)) { ent = kEmpty; break; }
+                    if (tries > (1u << 26)) { atomicExch(&st->error, 6u); ent = kEmpty; break; }
+                }
+            }
+            __syncwarp();
+        }
+        removed += warp_batch<kDist>(ent, k, row_ptr, col, deg, Q, cap, st, sh, part, tn, n_shared);
+        ++batches;
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd(&sh.r_done, m); }
+    }
+    n_shared = warp_reduce_add(n_shared);
+    if (lane == 0) {
+        if (removed) atomicAdd(&sh.removed, removed);
+        if (n_shared) atomicAdd(&sh.shared_cnt, n_shared);
+        atomicAdd(&sh.batches, batches);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (sh.shared_cnt) atomicAdd(&st->shared, (unsigned long long)sh.shared_cnt);
+        if (sh.batches) atomicAdd(&st->batches, (unsigned long long)sh.batches);
+    }
+    const uint32_t total_removed = sh.removed;
+    __syncthreads();  // sh is re-initialised by the next call
+    return total_removed;
+}
+
+}  // namespace peel
+}  // namespace kg
