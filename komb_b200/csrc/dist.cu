@@ -371,7 +371,7 @@ int kombgpu_part_peel_scan(kombgpu_part *p, int32_t k, uint32_t *n_front, uint32
     const uint32_t *src = p->alive_cur < 0 ? nullptr : p->alive[p->alive_cur];
     const int dst_i = p->alive_cur < 0 ? 0 : (p->alive_cur ^ 1);
     if (p->n_alive) {
-        uint32_t grid = min(ceil_div_u64(p->n_alive, kScanTileV), (uint32_t)p->grid);
+        uint32_t grid = min(ceil_div_u64(p->n_alive, kPeelThreads), (uint32_t)p->grid);  // scan_alive spreads short lists over the CTAs
         KG_LAUNCH(ctx, part_scan_kernel, grid, kPeelThreads, 0, k, src, p->n_alive, p->alive[dst_i], p->core, p->pool, p->state);
     }
     PeelState res{};

@@ -38,14 +38,16 @@ namespace {
 
 using namespace peel;
 
+constexpr unsigned long long kTraceWords = 16;   // words per round of the optional trace
+
 union PeelShared {
     BlockShared cta;   // scan phase (both modes) and the CTA-wide process phase
     WarpShared warp;   // warp-autonomous process phase (the phases are separated by grid barriers)
 };
 
-template <bool kWarpMode>
+template <bool kWarpMode, int kU>
 __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const uint64_t *__restrict__ row_ptr,
-                                                            const uint32_t *__restrict__ col, int32_t *deg,
+                                                            const uint32_t *__restrict__ col, int32_t *deg, int32_t *core_out,
                                                             uint64_t *Q, uint32_t cap, uint32_t *alive_a, uint32_t *alive_b,
                                                             PeelState *st) {
     cg::grid_group grid = cg::this_grid();
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
     uint32_t *alive_dst = alive_a;
     uint32_t round = 0;
     uint32_t removed = 0;                 // vertices this CTA peeled
+    uint32_t pool_base = 0;               // pool position at the end of the last level
 
     while (true) {
         const uint32_t par = round % 3;
@@ -72,10 +75,12 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         }
         const bool prof = (blockIdx.x == 0 && tid == 0);
         unsigned long long tp0 = prof ? global_ns() : 0;
+        long long stamps[6] = {0, 0, 0, 0, 0, 0};
         int32_t local_min = scan_alive(k, alive_src, n_alive, alive_dst, deg, Q, &st->q_tail, &st->front_cnt[par],
-                                       &st->alive_out[par], &st->n_isolated, sh);
+                                       &st->alive_out[par], &st->n_isolated, sh, (prof && st->trace) ? stamps : nullptr);
         local_min = warp_reduce_min(local_min);
         if (lane == 0 && local_min != INT32_MAX) atomicMin(&st->next_min[par], local_min);
+        if (prof) stamps[5] = clock64();
         unsigned long long tp1 = prof ? global_ns() : 0;
         grid.sync();
         unsigned long long tp2 = prof ? global_ns() : 0;
@@ -91,8 +96,10 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         ++round;
         const uint32_t trace_row = round - 1;
         if (prof && st->trace && trace_row < st->trace_cap) {
-            unsigned long long *tr = st->trace + 6ull * trace_row;
+            unsigned long long *tr = st->trace + kTraceWords * trace_row;
             tr[0] = (unsigned long long)(uint32_t)k; tr[1] = front_cnt; tr[2] = survivors; tr[3] = tp1 - tp0; tr[4] = 0; tr[5] = 0;
+            // SM cycles inside CTA 0's scan: id loads, degree gather, CTA scan + counters, stores + tail
+            tr[6] = stamps[1] - stamps[0]; tr[7] = stamps[2] - stamps[1]; tr[8] = stamps[3] - stamps[2]; tr[9] = stamps[5] - stamps[3];
         }
         if (front_cnt == 0) {
             // empty level: nothing to process; jump to the smallest remaining degree
@@ -106,18 +113,22 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         }
 
         // ---------------- PROCESS ----------------
-        if (kWarpMode) removed += process_level_warp<false>(k, round, Q, cap, row_ptr, col, deg, st, shu.warp, PartView{});
+        if (kWarpMode) {
+            // the scan appended the frontier at the pool position the last level ended at
+            removed += process_level_warp<false, kU>(k, round, Q, cap, row_ptr, col, deg, core_out, st, shu.warp, PartView{}, pool_base, front_cnt);
+        }
         else removed += process_level<false>(k, round, Q, cap, row_ptr, col, deg, st, sh, PartView{});
         unsigned long long tp3 = prof ? global_ns() : 0;
         grid.sync();
         if (prof) {
             const unsigned long long tp4 = global_ns();
             st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += tp4 - tp3;
-            if (st->trace && trace_row < st->trace_cap) { st->trace[6ull * trace_row + 4] = tp3 - tp2; st->trace[6ull * trace_row + 5] = tp4 - tp3; }
+            if (st->trace && trace_row < st->trace_cap) { st->trace[kTraceWords * trace_row + 4] = tp3 - tp2; st->trace[kTraceWords * trace_row + 5] = tp4 - tp3; }
         }
         // q_done == q_tail here and nothing moves until the next PROCESS phase
         if (__ldcg(&st->error)) break;
-        if (blockIdx.x == 0 && tid == 0) st->q_head = __ldcg(&st->q_done);  // un-reserve the slots past the tail
+        pool_base = __ldcg(&st->q_done);  // == q_tail, and stable until the next PROCESS phase starts
+        if (blockIdx.x == 0 && tid == 0) st->q_head = pool_base;  // un-reserve the slots past the tail
         k += 1;
     }
     if (tid == 0 && removed) atomicAdd(&st->n_removed, (unsigned long long)removed);
@@ -136,17 +147,30 @@ int peel_coreness(kombgpu_graph *g) {
         if (!g->core) return ctx_fail(ctx, KOMBGPU_ENOMEM, "coreness array");
     }
     if (n == 0) { g->has_core = true; return KOMBGPU_OK; }
-    KG_CUDA(ctx, cudaMemcpyAsync(g->core, g->deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
 
     const char *mode_env = getenv("KOMBGPU_PEEL_MODE");   // "cta": the CTA-wide process phase (kept for A/B measurements)
     const bool warp_mode = !(mode_env && mode_env[0] == 'c');
-    void *kernel = warp_mode ? (void *)peel_kernel<true> : (void *)peel_kernel<false>;
+    const char *unroll_env = getenv("KOMBGPU_PEEL_UNROLL");
+    const bool unroll8 = unroll_env && atoi(unroll_env) == 8;
+    void *kernel = !warp_mode ? (void *)peel_kernel<false, 4> : unroll8 ? (void *)peel_kernel<true, 8> : (void *)peel_kernel<true, 4>;
     int per_sm = 0;
-    if (warp_mode) KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<true>, kPeelThreads, 0));
-    else KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<false>, kPeelThreads, 0));
+    if (!warp_mode) KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<false, 4>, kPeelThreads, 0));
+    else if (unroll8) KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<true, 8>, kPeelThreads, 0));
+    else KG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peel_kernel<true, 4>, kPeelThreads, 0));
     if (per_sm < 1) return ctx_fail(ctx, KOMBGPU_ECUDA, "peel kernel does not fit on an SM");
     const int grid = per_sm * ctx->sm_count;  // persistent: every CTA resident (cooperative launch)
 
+    // warp mode: working degrees in a scratch array (never clamped), coreness written to g->core as vertices are
+    // taken (degree-0 vertices are peeled by the scan alone: their 0 comes from the memset);
+    // cta mode: g->core holds the working degrees, clamped at the current level, and ends as the coreness
+    DevBuf<int32_t> work;
+    int32_t *deg_work = g->core;
+    if (warp_mode) {
+        KG_ALLOC(ctx, work, n);
+        deg_work = work.p;
+        KG_CUDA(ctx, cudaMemsetAsync(g->core, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+    }
+    KG_CUDA(ctx, cudaMemcpyAsync(deg_work, g->deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     DevBuf<uint32_t> alive_a, alive_b;
     DevBuf<uint64_t> pool;
     DevBuf<PeelState> state(ctx, 1);
@@ -175,8 +199,8 @@ int peel_coreness(kombgpu_graph *g) {
     const char *trace_path = getenv("KOMBGPU_TRACE");
     const uint32_t trace_cap = 1u << 16;
     if (trace_path) {
-        KG_ALLOC(ctx, trace, 6ull * trace_cap);
-        KG_CUDA(ctx, cudaMemsetAsync(trace.p, 0, 6ull * trace_cap * sizeof(unsigned long long), ctx->stream));
+        KG_ALLOC(ctx, trace, kTraceWords * trace_cap);
+        KG_CUDA(ctx, cudaMemsetAsync(trace.p, 0, kTraceWords * trace_cap * sizeof(unsigned long long), ctx->stream));
         init.trace = trace.p;
         init.trace_cap = trace_cap;
     }
@@ -185,12 +209,13 @@ int peel_coreness(kombgpu_graph *g) {
     uint32_t n_arg = n;
     const uint64_t *row_ptr = g->row_ptr;
     const uint32_t *col = g->col;
-    int32_t *core = g->core;
+    int32_t *core = deg_work;
+    int32_t *core_out = g->core;
     uint32_t *aa = alive_a.p, *ab = alive_b.p;
     uint64_t *q = pool.p;
     uint32_t cap_arg = cap;
     PeelState *sp = state.p;
-    void *args[] = {&n_arg, &row_ptr, &col, &core, &q, &cap_arg, &aa, &ab, &sp};
+    void *args[] = {&n_arg, &row_ptr, &col, &core, &core_out, &q, &cap_arg, &aa, &ab, &sp};
     cudaEvent_t ev0, ev1;
     KG_CUDA(ctx, cudaEventCreate(&ev0));
     KG_CUDA(ctx, cudaEventCreate(&ev1));
@@ -212,12 +237,14 @@ int peel_coreness(kombgpu_graph *g) {
                 fin.prof_ns[2] * 1e-6, fin.prof_ns[3] * 1e-6, fin.batches, fin.shared, fin.sliced);
     if (trace_path) {
         const uint32_t rows = fin.rounds < trace_cap ? fin.rounds : trace_cap;
-        std::vector<unsigned long long> h(6ull * rows);
+        std::vector<unsigned long long> h(kTraceWords * rows);
         KG_CUDA(ctx, cudaMemcpy(h.data(), trace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE *f = fopen(trace_path, "w")) {
-            fprintf(f, "round,k,frontier,survivors,scan_ns,process_ns,wait_ns\n");
-            for (uint32_t r = 0; r < rows; ++r)
-                fprintf(f, "%u,%llu,%llu,%llu,%llu,%llu,%llu\n", r, h[6 * r], h[6 * r + 1], h[6 * r + 2], h[6 * r + 3], h[6 * r + 4], h[6 * r + 5]);
+            fprintf(f, "round,k,frontier,survivors,scan_ns,process_ns,wait_ns,scan_cyc_ids,scan_cyc_deg,scan_cyc_counters,scan_cyc_tail,p_init,p_first,p_lastdone,p_over,p_exit\n");
+            for (uint32_t r = 0; r < rows; ++r) {
+                const unsigned long long *t = &h[kTraceWords * r];
+                fprintf(f, "%u,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", r, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], t[10], t[11], t[12], t[13], t[14]);
+            }
             fclose(f);
         }
     }

@@ -15,7 +15,9 @@
 // shuffle-based search of the row prefix, four independent chains per lane.
 //
 // The global pool protocol of peel_device.cuh is unchanged, but it is spoken by ONE warp per CTA at a time, the
-// AGENT: the parked warp that owns the ticket r_tail (the slot the next push will fill).  When the CTA is locally
+// AGENT: the parked warp that holds the LAST reservation (its range ends at r_head), so that discoveries of the
+// CTA's own warps are handed to plain parked warps first (they poll shared memory only; the agent may be waiting
+// for a global load) and work the agent brings in reaches every other parked warp before itself.  When the CTA is locally
 // quiescent (r_done == r_tail) the agent settles the CTA's credit with q_done, detects the end of the level, or
 // claims / reserves pool slots.  Pool entries known to be below q_tail are handed to the workers as RANGE
 // descriptors (one ring ticket = up to 32 pool entries, loaded by the worker itself), reserved pool slots are
@@ -33,8 +35,9 @@ constexpr uint32_t kRingMask = kRing - 1;
 constexpr int32_t kRingKeep = 16;         // default of WarpTune::keep
 constexpr uint64_t kRangeBit = 1ull << 62;  // ring-only entry: kRangeBit | first_pool_slot << 8 | count
 constexpr uint32_t kRangeLen = 32;
-constexpr uint32_t kWarpSplit = 256;       // default of WarpTune::wsplit
+constexpr uint32_t kWarpSplit = 128;       // default of WarpTune::wsplit
 constexpr uint32_t kWarpSplitMin = 128;    // lower bound of the knob (sizes the pool)
+constexpr uint32_t kStaticMax = 16 * kRangeLen;  // frontier entries dealt to a CTA without a claim
 constexpr uint32_t kSpinCheck = 1u << 16;  // polls between two looks at the watchdog clock
 
 // run-time knobs (PeelState::tune; defaults below, overridable through KOMBGPU_PEEL_* for measurements)
@@ -55,6 +58,8 @@ struct WarpShared {
     uint32_t removed;
     uint32_t shared_cnt;
     uint32_t batches;
+    uint32_t spare;
+    long long t[6];       // CTA 0, trace only: entry, init done, first batch, last batch end, level over, exit
 };
 
 __device__ __forceinline__ uint32_t lds_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
@@ -73,11 +78,11 @@ __device__ __forceinline__ void ring_put(WarpShared &sh, uint32_t ticket, uint64
 
 // One batch of a warp: lane i holds task `ent` (a vertex, a slice of a hub row, or kEmpty).  Returns how many
 // vertices were peeled.
-template <bool kDist>
+template <bool kDist, int kU>
 __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t k, const uint64_t *__restrict__ row_ptr,
-                                               const uint32_t *__restrict__ col, int32_t *deg, uint64_t *Q, const uint32_t cap,
-                                               PeelState *st, WarpShared &sh, const PartView &part, const WarpTune &tn,
-                                               uint32_t &n_shared) {
+                                               const uint32_t *__restrict__ col, int32_t *deg, int32_t *core_out, uint64_t *Q,
+                                               const uint32_t cap, PeelState *st, WarpShared &sh, const PartView &part,
+                                               const WarpTune &tn, uint32_t &n_shared) {
     const uint32_t lane = lane_id();
     uint32_t my_len = 0;
     uint64_t my_row = 0;
@@ -89,6 +94,7 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
         } else {
             const uint32_t v = (uint32_t)ent;
             is_vertex = true;
+            core_out[v] = k;   // peeled at level k
             my_row = row_ptr[v];
             my_len = (uint32_t)(row_ptr[v + 1] - my_row);
             if (my_len > kSplit) {
@@ -119,16 +125,33 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
                 to_pool = (queued >= tn.keep || xtot > 128u) ? 1u : 0u;
                 pos = to_pool ? atomicAdd(&st->q_tail, xtot) : atomicAdd(&sh.r_tail, xtot);
             }
-            pos = __shfl_sync(kFullMask, pos, 0) + (xin - extra);
+            pos = __shfl_sync(kFullMask, pos, 0);
             to_pool = __shfl_sync(kFullMask, to_pool, 0);
-            for (uint32_t i = 1; i <= extra; ++i, ++pos) {
-                const uint64_t e = kSliceBit | ((my_row + (uint64_t)i * tn.wsplit) << kSliceLenBits) |
-                                   min(tn.wsplit, my_len - i * tn.wsplit);
-                if (to_pool) {
-                    if (pos < cap) st_volatile_u64(&Q[pos], e);
-                    else atomicExch(&st->error, 3u);
-                } else {
-                    ring_put(sh, pos, e);
+            // the xtot tickets are written by all lanes together (ticket t belongs to the first row j with
+            // xin[j] > t): one lane writing the 30 pieces of a 4096-edge row costs more than walking a piece
+            const uint32_t rlo = (uint32_t)my_row, rhi = (uint32_t)(my_row >> 32);
+            for (uint32_t tb = 0; tb < xtot; tb += 32) {
+                const uint32_t t = tb + lane;
+                uint32_t j = 0;
+#pragma unroll
+                for (uint32_t sft = 16; sft > 0; sft >>= 1) {
+                    const uint32_t x = __shfl_sync(kFullMask, xin, (j + sft - 1) & 31u);
+                    if (x <= t) j += sft;
+                }
+                j &= 31u;
+                const uint32_t j_xin = __shfl_sync(kFullMask, xin, j), j_extra = __shfl_sync(kFullMask, extra, j);
+                const uint32_t j_len = __shfl_sync(kFullMask, my_len, j);
+                const uint64_t j_row = ((uint64_t)__shfl_sync(kFullMask, rhi, j) << 32) | __shfl_sync(kFullMask, rlo, j);
+                if (t < xtot) {
+                    const uint32_t i = t - (j_xin - j_extra) + 1;   // piece 1..extra of row j (piece 0 stays here)
+                    const uint64_t e = kSliceBit | ((j_row + (uint64_t)i * tn.wsplit) << kSliceLenBits) |
+                                       min(tn.wsplit, j_len - i * tn.wsplit);
+                    if (to_pool) {
+                        if (pos + t < cap) st_volatile_u64(&Q[pos + t], e);
+                        else atomicExch(&st->error, 3u);
+                    } else {
+                        ring_put(sh, pos + t, e);
+                    }
                 }
             }
             if (extra) my_len = tn.wsplit;
@@ -138,14 +161,14 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
     const uint32_t excl = incl - my_len;
     const uint32_t total = __shfl_sync(kFullMask, incl, 31);
     const uint32_t row_lo = (uint32_t)my_row, row_hi = (uint32_t)(my_row >> 32);
-    const bool direct = total <= 32u * kUnroll;
+    const bool direct = total <= 32u * kU;
 
-    for (uint32_t base = 0; base < total; base += 32u * kUnroll) {
-        uint32_t u[kUnroll];
-        int32_t d[kUnroll];
-        bool push[kUnroll];
+    for (uint32_t base = 0; base < total; base += 32u * kU) {
+        uint32_t u[kU];
+        int32_t d[kU];
+        bool push[kU];
 #pragma unroll
-        for (int t = 0; t < kUnroll; ++t) {
+        for (int t = 0; t < kU; ++t) {
             const uint32_t e = base + t * 32u + lane;
             // owner row: the last lane j with excl[j] <= e (rows of length 0 are skipped by "last")
             uint32_t j = 0;
@@ -162,7 +185,7 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
         if (kDist) {
             // split off the neighbours other ranks own: ship their ids, keep local ones as local ids
 #pragma unroll
-            for (int t = 0; t < kUnroll; ++t) {
+            for (int t = 0; t < kU; ++t) {
                 const bool valid = u[t] != kFullMask;
                 const uint32_t loc = u[t] - part.v_lo;
                 const bool remote = valid && loc >= part.n_local;
@@ -176,32 +199,26 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
                 u[t] = (valid && !remote) ? loc : kFullMask;
             }
         }
+        // deg[] is NOT clamped in this mode (the coreness goes to core_out when a vertex is taken): a decrement is
+        // one fire-and-look atomic, never undone, never preceded by a load.  deg[u] passes k + 1 -> k exactly once,
+        // and the thread that sees it owns u.  (Decrements of vertices already peeled are wasted, not wrong: a
+        // vertex receives at most one per neighbour, so deg stays >= 0.)
         if (direct) {
-            // latency-bound batch (one iteration): the decrement goes out right away and is undone if it lands
-            // at or below k -- one dependent round trip less on the cascade's critical path
+            // latency-bound batch (one iteration): no look before the decrement
 #pragma unroll
-            for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? atomicSub(&deg[u[t]], 1) : INT32_MAX;
-#pragma unroll
-            for (int t = 0; t < kUnroll; ++t) {
-                push[t] = d[t] == k + 1;
-                if (d[t] <= k) atomicAdd(&deg[u[t]], 1);
-            }
+            for (int t = 0; t < kU; ++t) d[t] = (u[t] != kFullMask) ? atomicSub(&deg[u[t]], 1) : INT32_MAX;
         } else {
+            // throughput-bound batch: a load is cheaper than an atomic on a vertex that is already gone
 #pragma unroll
-            for (int t = 0; t < kUnroll; ++t) d[t] = (u[t] != kFullMask) ? __ldcg(&deg[u[t]]) : INT32_MIN;
+            for (int t = 0; t < kU; ++t) d[t] = (u[t] != kFullMask) ? __ldcg(&deg[u[t]]) : INT32_MIN;
 #pragma unroll
-            for (int t = 0; t < kUnroll; ++t) {
-                push[t] = false;
-                if (d[t] > k) {
-                    const int32_t old = atomicSub(&deg[u[t]], 1);
-                    if (old == k + 1) push[t] = true;             // u just reached level k: ours to peel
-                    else if (old <= k) atomicAdd(&deg[u[t]], 1);  // already at level k: undo (clamp)
-                }
-            }
+            for (int t = 0; t < kU; ++t) d[t] = (d[t] > k) ? atomicSub(&deg[u[t]], 1) : INT32_MAX;
         }
+#pragma unroll
+        for (int t = 0; t < kU; ++t) push[t] = d[t] == k + 1;
         uint32_t c = 0;
 #pragma unroll
-        for (int t = 0; t < kUnroll; ++t) c += push[t] ? 1u : 0u;
+        for (int t = 0; t < kU; ++t) c += push[t] ? 1u : 0u;
         if (__ballot_sync(kFullMask, c != 0) == 0) continue;
         const uint32_t inc = warp_incl_scan_add(c);
         const uint32_t tot = __shfl_sync(kFullMask, inc, 31);
@@ -215,7 +232,7 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
         to_pool = __shfl_sync(kFullMask, to_pool, 0);
         if (to_pool) n_shared += c;
 #pragma unroll
-        for (int t = 0; t < kUnroll; ++t) {
+        for (int t = 0; t < kU; ++t) {
             if (!push[t]) continue;
             if (to_pool) {
                 if (pos < cap) st_volatile_u64(&Q[pos], (uint64_t)u[t]);
@@ -232,7 +249,7 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const int32_t
 // One step of the agent (whole warp, sh.lock held by lane 0).  Either delivers work into the ring, ends the level
 // (sh.over), or does nothing because other warps of the CTA are still working.
 __device__ __forceinline__ void agent_step(const uint64_t token, uint64_t *Q, const uint32_t cap, PeelState *st, WarpShared &sh,
-                                           unsigned long long &idle_since) {
+                                           const uint32_t dealt, unsigned long long &idle_since) {
     const uint32_t lane = lane_id();
     const uint32_t gb = lds_u32(&sh.gb), ge = lds_u32(&sh.ge);
     // 1. reserved pool slots: copy the leading run of written ones into the ring
@@ -268,41 +285,45 @@ __device__ __forceinline__ void agent_step(const uint64_t token, uint64_t *Q, co
         const uint32_t tl = lds_u32(&sh.r_tail);
         quiet = dn == tl ? 1u : 0u;
     }
-    if (!__shfl_sync(kFullMask, quiet, 0)) return;
-    // 3. the CTA is drained: settle its credit, then end the level, keep waiting, or claim / reserve pool slots
+    quiet = __shfl_sync(kFullMask, quiet, 0);
+    // a busy CTA with an idle warp listens on reserved pool slots too (work goes where idle warps are); it
+    // cannot end the level and has nothing to settle
+    if (!quiet && gb < ge) return;
+    // 3. settle the credit of a drained CTA; then end the level, keep waiting, or claim / reserve pool slots
     uint32_t over = 0, fin_tail = 0, fin_head = 0, begin = 0, sure = 0, end = 0;
     if (lane == 0) {
-        const uint32_t credit = lds_u32(&sh.credit);
+        const uint32_t credit = quiet ? lds_u32(&sh.credit) : 0u;
         uint4 a = make_uint4(0, 0, 0, 0);
         bool have_a = false;
         if (credit) {
             __threadfence();
             const uint32_t old = atomicAdd(&st->q_done, credit);
             a = ld_volatile_u4(st);  // q_head, q_tail, q_done, error
+            a.x += dealt;            // q_head counts claims only: the statically dealt entries come on top
             have_a = true;
             sts_u32(&sh.credit, 0);
             if (old + credit == a.y) { fin_tail = a.y; fin_head = min(a.x, cap); over = 1; }  // quiescent, final
         }
         if (!over) {
             if (gb < ge) {
-                // parked on reserved slots: only rarely look at the shared counters
+                // drained and parked on reserved slots: only rarely look at the shared counters
                 const uint32_t polls = lds_u32(&sh.polls) + 1;
                 sts_u32(&sh.polls, polls);
                 if (have_a || polls == 1 || (polls & 7u) == 0) {
-                    if (!have_a) a = ld_volatile_u4(st);
+                    if (!have_a) { a = ld_volatile_u4(st); a.x += dealt; }
                     if (a.z == a.y || a.w) over = 1;  // q_done == q_tail: final, nobody can append any more
                     else if (idle_since == 0) idle_since = global_ns();
                     else if (global_ns() - idle_since > kWatchdogNs) { atomicExch(&st->error, 2u); over = 1; }
                 }
                 if (!over) __nanosleep(100);
             } else {
-                if (!have_a) a = ld_volatile_u4(st);
-                if (a.z == a.y || a.w) {
+                if (!have_a) { a = ld_volatile_u4(st); a.x += dealt; }
+                if (a.w || (quiet && a.z == a.y)) {
                     over = 1;
                 } else {
                     uint32_t take = 1;
                     if (a.x < a.y) take = min(max((a.y - a.x + gridDim.x - 1) / gridDim.x, 1u), kClaimMax);
-                    begin = atomicAdd(&st->q_head, take);
+                    begin = atomicAdd(&st->q_head, take) + dealt;
                     end = min(begin + take, cap);
                     if (begin >= cap) { atomicExch(&st->error, 4u); over = 1; end = begin; }
                     sure = min(max(a.y, begin), end);  // slots below the tail seen before the claim: written, or about to be
@@ -324,14 +345,16 @@ __device__ __forceinline__ void agent_step(const uint64_t token, uint64_t *Q, co
         return;
     }
     if (end > begin) {
-        const uint32_t n_desc = (sure - begin + kRangeLen - 1) / kRangeLen;
+        // spread the claimed entries over all warps of the CTA: ranges of ceil(count / warps), at most kRangeLen
+        const uint32_t rl = min(max((sure - begin + kPeelWarps - 1) / kPeelWarps, 1u), kRangeLen);
+        const uint32_t n_desc = (sure - begin + rl - 1) / rl;
         if (n_desc) {
             uint32_t pos = 0;
             if (lane == 0) pos = atomicAdd(&sh.r_tail, n_desc);
             pos = __shfl_sync(kFullMask, pos, 0);
             for (uint32_t i = lane; i < n_desc; i += 32) {
-                const uint32_t s = begin + i * kRangeLen;
-                ring_put(sh, pos + i, kRangeBit | ((uint64_t)s << 8) | (uint64_t)min(kRangeLen, sure - s));
+                const uint32_t s = begin + i * rl;
+                ring_put(sh, pos + i, kRangeBit | ((uint64_t)s << 8) | (uint64_t)min(rl, sure - s));
             }
         }
         if (lane == 0) {
@@ -344,20 +367,40 @@ __device__ __forceinline__ void agent_step(const uint64_t token, uint64_t *Q, co
 }
 
 // PROCESS phase of one level for one CTA (all kPeelThreads threads call it; returns the vertices the CTA peeled).
-template <bool kDist>
+template <bool kDist, int kU = kUnroll>
 __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const uint32_t round, uint64_t *Q, const uint32_t cap,
                                                        const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
-                                                       int32_t *deg, PeelState *st, WarpShared &sh, const PartView &part) {
+                                                       int32_t *deg, int32_t *core_out, PeelState *st, WarpShared &sh,
+                                                       const PartView &part, const uint32_t front_base = 0,
+                                                       const uint32_t front_cnt = 0) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
     const uint64_t token = ((uint64_t)kTokenHi << 32) | round;
     for (uint32_t i = tid; i < (uint32_t)kRing; i += kPeelThreads) sh.ring[i] = kEmpty;
+    // The level's frontier is pool[front_base, front_base + front_cnt), complete before this phase (grid barrier).
+    // Its first grid x S entries are dealt statically, S = min(ceil(front_cnt / grid), kStaticMax) per CTA: no
+    // claim, no look at the shared counters on the way to the first edge.  q_head keeps counting claims only (it
+    // starts every level at front_base), so every slot index derived from it is offset by `dealt`.
+    const uint32_t S = min((front_cnt + gridDim.x - 1) / gridDim.x, kStaticMax);
+    const uint32_t dealt = min(front_cnt, gridDim.x * S);
+    const uint32_t my_lo = front_base + min(blockIdx.x * S, dealt), my_hi = front_base + min((blockIdx.x + 1) * S, dealt);
+    const bool prof = blockIdx.x == 0 && st->trace != nullptr;
     if (tid == 0) {
+        if (prof) { sh.t[0] = clock64(); sh.t[2] = 0; sh.t[3] = 0; sh.t[4] = 0; }
         sh.r_head = 0; sh.r_tail = 0; sh.r_done = 0;
-        sh.over = 0; sh.lock = 0; sh.credit = 0; sh.gb = 0; sh.ge = 0; sh.polls = 0;
+        sh.over = 0; sh.lock = 0; sh.credit = my_hi - my_lo; sh.gb = 0; sh.ge = 0; sh.polls = 0;
         sh.removed = 0; sh.shared_cnt = 0; sh.batches = 0;
     }
     __syncthreads();
+    if (my_hi > my_lo && tid < 32) {
+        const uint32_t cnt = my_hi - my_lo;
+        const uint32_t rl = min(max((cnt + kPeelWarps - 1) / kPeelWarps, 1u), kRangeLen);
+        const uint32_t n_desc = (cnt + rl - 1) / rl;   // <= 16 (kStaticMax = 16 x kRangeLen)
+        if (lane < n_desc) sh.ring[lane] = kRangeBit | ((uint64_t)(my_lo + lane * rl) << 8) | (uint64_t)min(rl, cnt - lane * rl);
+        if (lane == 0) sh.r_tail = n_desc;
+    }
+    __syncthreads();
 
+    if (prof && tid == 0) sh.t[1] = clock64();
     WarpTune tn;
     tn.keep = (int32_t)st->tune[0];
     tn.wsplit = st->tune[1];
@@ -388,14 +431,14 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
             uint32_t act = 0;  // 1: leave, 2: act as the agent
             if (lane == 0) {
                 if (lds_u32(&sh.over)) act = 1;
-                else if (lds_u32(&sh.r_tail) == rb && atomicCAS(&sh.lock, 0u, 1u) == 0u)
-                    // re-check under the lock: the slot may have been filled, the level may have ended
-                    act = (lds_u32(&sh.r_tail) == rb && !lds_u32(&sh.over)) ? 2u : 3u;
+                else if (lds_u32(&sh.r_head) == re && atomicCAS(&sh.lock, 0u, 1u) == 0u)
+                    // re-check under the lock: another warp may have parked behind this one, the level may have ended
+                    act = (lds_u32(&sh.r_head) == re && !lds_u32(&sh.over)) ? 2u : 3u;
             }
             act = __shfl_sync(kFullMask, act, 0);
             if (act == 1) break;
             if (act >= 2) {
-                if (act == 2) agent_step(token, Q, cap, st, sh, idle_since);
+                if (act == 2) agent_step(token, Q, cap, st, sh, dealt, idle_since);
                 __syncwarp();
                 if (lane == 0) { __threadfence_block(); atomicExch(&sh.lock, 0u); }
             } else {
@@ -408,6 +451,7 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
             continue;
         }
         idle_since = 0;
+        if (prof && lane == 0 && sh.t[2] == 0) sh.t[2] = clock64();
         // a range descriptor is a batch of its own
         const uint32_t dm = __ballot_sync(kFullMask, ent != kEmpty && (ent & kSliceBit) == 0 && (ent & kRangeBit) != 0) & ((m == 32u) ? kFullMask : ((1u << m) - 1u));
         bool is_range = false;
@@ -431,11 +475,12 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
             }
             __syncwarp();
         }
-        removed += warp_batch<kDist>(ent, k, row_ptr, col, deg, Q, cap, st, sh, part, tn, n_shared);
+        removed += warp_batch<kDist, kU>(ent, k, row_ptr, col, deg, core_out, Q, cap, st, sh, part, tn, n_shared);
         ++batches;
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); atomicAdd(&sh.r_done, m); }
+        if (lane == 0) { __threadfence_block(); atomicAdd(&sh.r_done, m); if (prof) sh.t[3] = clock64(); }
     }
+    if (prof && lane == 0 && sh.t[4] == 0) sh.t[4] = clock64();
     n_shared = warp_reduce_add(n_shared);
     if (lane == 0) {
         if (removed) atomicAdd(&sh.removed, removed);
@@ -448,6 +493,14 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
         if (sh.batches) atomicAdd(&st->batches, (unsigned long long)sh.batches);
     }
     const uint32_t total_removed = sh.removed;
+    if (prof && tid == 0) {
+        sh.t[5] = clock64();
+        unsigned long long *tr = st->trace + 16ull * (round - 1);   // peel.cu: kTraceWords = 16, row = round - 1
+        if (round - 1 < st->trace_cap) {
+            tr[10] = sh.t[1] - sh.t[0]; tr[11] = sh.t[2] ? sh.t[2] - sh.t[1] : 0; tr[12] = sh.t[3] ? sh.t[3] - sh.t[1] : 0;
+            tr[13] = sh.t[4] - sh.t[1]; tr[14] = sh.t[5] - sh.t[1];
+        }
+    }
     __syncthreads();  // sh is re-initialised by the next call
     return total_removed;
 }

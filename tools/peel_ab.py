@@ -17,12 +17,9 @@ VARIANTS = [
     ("cta", {"KOMBGPU_PEEL_MODE": "cta"}),
     ("warp", {"KOMBGPU_PEEL_MODE": "warp"}),
     ("warp keep4", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "4"}),
-    ("warp keep64", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "64"}),
-    ("warp park50", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "50"}),
-    ("warp wsplit128", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_WSPLIT": "128"}),
-    ("warp wsplit512", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_WSPLIT": "512"}),
+    ("warp wsplit256", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_WSPLIT": "256"}),
 ]
-KNOBS = ["KOMBGPU_PEEL_MODE", "KOMBGPU_PEEL_KEEP", "KOMBGPU_PEEL_PARK", "KOMBGPU_PEEL_WSPLIT"]
+KNOBS = ["KOMBGPU_PEEL_MODE", "KOMBGPU_PEEL_KEEP", "KOMBGPU_PEEL_PARK", "KOMBGPU_PEEL_WSPLIT", "KOMBGPU_PEEL_UNROLL"]
 
 
 def make_graph(ctx, w):
