@@ -256,6 +256,13 @@ int kombgpu_corea_dev(kombgpu_ctx *ctx, const int32_t *coreness_dev, const int32
 
 int kombgpu_abi_version(void);
 
+/* Measurement aid (tools/sort_probe.py): sorts n synthetic 64-bit keys with lo_bits random low bits and
+ * hi_bits bits at position 32 (random, or non-decreasing when sorted_hi != 0: the shape of hit arrays in
+ * read order) on bits [0, lo_bits) + [32, 32 + hi_bits), `reps` times; returns the best time of the sort
+ * alone and whether the result is a sorted permutation of the input.  Replaces nothing in the reference. */
+int kombgpu_debug_sort_u64(kombgpu_ctx *ctx, uint64_t n, int lo_bits, int hi_bits, int sorted_hi, int reps,
+                           float *ms_best, int *ok);
+
 #ifdef __cplusplus
 }
 #endif

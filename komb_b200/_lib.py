@@ -35,6 +35,7 @@ class Stats(ctypes.Structure):
 u32p, u64p, i32p, f64p = POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32), POINTER(c_double)
 SIGNATURES = {
     "kombgpu_abi_version": (c_int, []),
+    "kombgpu_debug_sort_u64": (c_int, [c_void_p, c_uint64, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_int)]),
     "kombgpu_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
     "kombgpu_ctx_destroy": (None, [c_void_p]),
     "kombgpu_ctx_set_stream": (c_int, [c_void_p, c_void_p]),

@@ -11,6 +11,8 @@
 // No atomics are needed anywhere in this stage: every count falls out of run
 // boundaries in sorted arrays, so the result (including the order inside each
 // CSR row) is deterministic.
+#include <cstdlib>
+
 #include "graph.cuh"
 #include "primitives.cuh"
 
@@ -24,24 +26,109 @@ inline uint32_t grid_for(uint64_t n, int per_block) { return ceil_div_u64(n ? n 
 
 // ---- packing ---------------------------------------------------------------
 
-// key = read_key << 32 | unitig; also the max read key (for the sort plan) and an
-// out-of-range flag.  info[0] = max read key, info[1] = error flag.
+// key = read_key << 32 | unitig; also the max read key (for the sort plan), an out-of-range flag, and how the
+// read keys are ordered: info[0] = max read key, info[1] = error flag, info[2] = number of descents
+// (read_key[i] < read_key[i-1]), info[3] = position of the first one.  SAM files list reads in input order, so the
+// two mate files arrive as two runs of non-decreasing keys (one descent, at the file boundary).
 __global__ void __launch_bounds__(kThreads) pack_hits_kernel(const uint32_t *__restrict__ read_key,
                                                              const uint32_t *__restrict__ unitig, uint64_t n_hits,
                                                              uint32_t n_vertices, uint64_t *__restrict__ keys,
                                                              uint32_t *__restrict__ info) {
-    uint32_t local_max = 0;
+    uint32_t local_max = 0, descents = 0, first = 0xffffffffu;
     bool bad = false;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_hits; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t r = read_key[i], u = unitig[i];
         bad |= (u >= n_vertices);
         local_max = max(local_max, r);
+        if (i > 0 && r < read_key[i - 1]) { ++descents; first = min(first, (uint32_t)i); }
         keys[i] = ((uint64_t)r << 32) | u;
     }
     local_max = warp_reduce_max(local_max);
-    if (lane_id() == 0 && local_max) atomicMax(&info[0], local_max);
+    descents = warp_reduce_add(descents);
+    first = warp_reduce_min(first);
+    if (lane_id() == 0) {
+        if (local_max) atomicMax(&info[0], local_max);
+        if (descents) { atomicAdd(&info[2], descents); atomicMin(&info[3], first); }
+    }
     if (__any_sync(kFullMask, bad) && lane_id() == 0) atomicOr(&info[1], 1u);
 }
+
+// ---- reads in file order: merge the two runs, no sort -----------------------------------------------------
+
+constexpr int kMergeItems = 8;
+constexpr int kMergeTile = kThreads * kMergeItems;
+
+__device__ __forceinline__ uint32_t read_of(uint64_t key) { return (uint32_t)(key >> 32); }
+
+// number of A elements among the first `diag` outputs of the stable merge (A before B on equal read keys)
+template <typename KeyA, typename KeyB>
+__device__ __forceinline__ uint32_t merge_path(uint32_t diag, uint32_t n_a, uint32_t n_b, KeyA key_a, KeyB key_b) {
+    uint32_t lo = diag > n_b ? diag - n_b : 0, hi = min(diag, n_a);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key_a(mid) <= key_b(diag - 1 - mid)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// part[t] = A elements before output t * kMergeTile
+__global__ void __launch_bounds__(kThreads) merge_partition_kernel(const uint64_t *__restrict__ a, uint32_t n_a,
+                                                                   const uint64_t *__restrict__ b, uint32_t n_b,
+                                                                   uint32_t n_tiles, uint32_t *__restrict__ part) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const uint32_t diag = (uint32_t)min((uint64_t)t * kMergeTile, (uint64_t)n_a + n_b);
+    part[t] = merge_path(diag, n_a, n_b, [&](uint32_t i) { return read_of(a[i]); }, [&](uint32_t j) { return read_of(b[j]); });
+}
+
+// stable merge by read key of two runs of packed hits; the unitigs of a read stay in arrival order
+__global__ void __launch_bounds__(kThreads) merge_runs_kernel(const uint64_t *__restrict__ a, uint32_t n_a,
+                                                              const uint64_t *__restrict__ b, uint32_t n_b,
+                                                              const uint32_t *__restrict__ part, uint64_t *__restrict__ out) {
+    __shared__ uint64_t s_key[kMergeTile];
+    const uint32_t tile = blockIdx.x;
+    const uint64_t o0 = (uint64_t)tile * kMergeTile;
+    const uint32_t count = (uint32_t)min((uint64_t)kMergeTile, (uint64_t)n_a + n_b - o0);
+    const uint32_t a0 = part[tile], a1 = part[tile + 1];
+    const uint32_t b0 = (uint32_t)(o0 - a0);
+    const uint32_t ca = a1 - a0, cb = count - ca;   // the tile's A keys sit at s_key[0, ca), its B keys behind them
+    for (uint32_t i = threadIdx.x; i < count; i += kThreads) s_key[i] = i < ca ? a[a0 + i] : b[b0 + (i - ca)];
+    __syncthreads();
+    const uint32_t diag = min(threadIdx.x * kMergeItems, count);
+    uint32_t ia = merge_path(diag, ca, cb, [&](uint32_t i) { return read_of(s_key[i]); },
+                             [&](uint32_t j) { return read_of(s_key[ca + j]); });
+    uint32_t ib = diag - ia;
+    uint64_t res[kMergeItems];
+#pragma unroll
+    for (int j = 0; j < kMergeItems; ++j) {
+        const bool has_a = ia < ca, has_b = ib < cb;
+        const uint64_t ka = has_a ? s_key[ia] : 0, kb = has_b ? s_key[ca + ib] : 0;
+        const bool take_a = has_a && (!has_b || read_of(ka) <= read_of(kb));
+        res[j] = take_a ? ka : kb;
+        if (take_a) ++ia; else ++ib;
+    }
+#pragma unroll
+    for (int j = 0; j < kMergeItems; ++j)
+        if (diag + j < count) out[o0 + diag + j] = res[j];
+}
+
+// hits grouped by read (unitigs in any order inside a read): 1 for the first occurrence of a (read, unitig).
+// A read longer than kMaxReadScan hits is left to the general sort path (*too_long is raised).
+constexpr uint32_t kMaxReadScan = 64;
+struct FirstInReadFlag {
+    const uint64_t *hits;
+    uint32_t *too_long;
+    __device__ uint32_t operator()(uint64_t i) const {
+        const uint64_t k = hits[i];
+        for (uint32_t back = 1; back <= i; ++back) {
+            const uint64_t p = hits[i - back];
+            if ((p >> 32) != (k >> 32)) return 1u;
+            if (p == k) return 0u;
+            if (back == kMaxReadScan) { atomicExch(too_long, 1u); return 1u; }
+        }
+        return 1u;
+    }
+};
 
 // canonical undirected key (min << 32 | max); loops keep u == v and are dropped
 // by the unique pass.
@@ -151,8 +238,8 @@ __global__ void __launch_bounds__(kThreads) emit_pairs_kernel(const uint64_t *__
         while ((b + 1) * b / 2 <= t) ++b;
         uint64_t a = t - b * (b - 1) / 2;
         const uint64_t h = s_head[lo];
-        uint32_t ua = (uint32_t)hits[h + a], ub = (uint32_t)hits[h + b];  // ua < ub: sorted unique within the read
-        pairs[p] = ((uint64_t)ua << 32) | ub;
+        const uint32_t ua = (uint32_t)hits[h + a], ub = (uint32_t)hits[h + b];  // distinct; ascending only after a sort
+        pairs[p] = ((uint64_t)min(ua, ub) << 32) | max(ua, ub);
     }
 }
 
@@ -293,28 +380,61 @@ int hits_to_sorted_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
 
     // 1. (read, unitig) keys, sorted + unique  == per-read unitig SETS, mates merged
     DevBuf<uint64_t> ha, hb;
-    DevBuf<uint32_t> info(ctx, 2);
+    DevBuf<uint32_t> info(ctx, 5);
     KG_ALLOC(ctx, ha, n_hits);
     KG_ALLOC(ctx, hb, n_hits);
     if (!info) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_CUDA(ctx, cudaMemsetAsync(info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    const uint32_t info0[5] = {0, 0, 0, 0xffffffffu, 0};   // max key, error, descents, first descent, read too long
+    KG_CUDA(ctx, cudaMemcpyAsync(info.p, info0, sizeof(info0), cudaMemcpyHostToDevice, ctx->stream));
     if (n_hits)
         KG_LAUNCH(ctx, pack_hits_kernel, min(grid_for(n_hits, kThreads), 148u * 16u), kThreads, 0, read_key, unitig, n_hits,
                   n_vertices, ha.p, info.p);
-    uint32_t h_info[2] = {0, 0};
-    KG_TRY(read_back(ctx, info.p, h_info, 2));
+    uint32_t h_info[5] = {0, 0, 0, 0, 0};
+    KG_TRY(read_back(ctx, info.p, h_info, 5));
     if (h_info[1]) return ctx_fail(ctx, KOMBGPU_EINVAL, "unitig id >= n_vertices (%u)", n_vertices);
-    uint64_t *sorted = ha.p;
-    RadixPass passes[8];
-    int np = plan_radix_passes(0, bn, 32, 32 + bits_for(h_info[0]), passes);
-    KG_TRY(radix_sort_u64(ctx, ha.p, hb.p, n_hits, passes, np, &sorted));
-    uint64_t *other = sorted == ha.p ? hb.p : ha.p;
     DevBuf<uint32_t> d_cnt(ctx, 1);
     if (!d_cnt) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_TRY((device_scan<uint32_t>(ctx, n_hits, HeadFlagU64{sorted}, CompactKeysU64{sorted, other}, d_cnt.p)));
+    uint64_t *sorted = ha.p, *other = hb.p;
     uint32_t n_uniq = 0;
-    KG_TRY(read_back(ctx, d_cnt.p, &n_uniq, 1));
-    const uint64_t *hits = other;  // sorted unique hits, n_uniq of them
+    RadixPass passes[8];
+    bool grouped = false;   // unique hits grouped by read without a sort?
+    DevBuf<uint64_t> hc;    // third buffer of the merge path (see below)
+    if (n_hits && h_info[2] <= 1 && !getenv("KOMBGPU_NO_MERGE")) {
+        // The reads arrive in file order (at most two runs of non-decreasing keys: the two mate files): a stable
+        // merge by read key replaces the radix sort (6 passes for cfg2), and since the per-read unitig SET is all
+        // the path needs, duplicates inside a read are found by looking back through the read.
+        uint64_t *by_read = ha.p;
+        if (h_info[2] == 1) {
+            const uint32_t n_a = h_info[3], n_b = (uint32_t)(n_hits - n_a);
+            const uint32_t n_tiles = ceil_div_u64(n_hits, kMergeTile);
+            DevBuf<uint32_t> part;
+            KG_ALLOC(ctx, part, (size_t)n_tiles + 1);
+            KG_LAUNCH(ctx, merge_partition_kernel, grid_for((uint64_t)n_tiles + 1, kThreads), kThreads, 0, ha.p, n_a, ha.p + n_a, n_b,
+                      n_tiles, part.p);
+            KG_LAUNCH(ctx, merge_runs_kernel, n_tiles, kThreads, 0, ha.p, n_a, ha.p + n_a, n_b, part.p, hb.p);
+            by_read = hb.p;
+        }
+        // compaction needs a third buffer only when the merge used both: the packed input is dead after the merge,
+        // but a read that is too long sends us back to it, so keep it and compact into scratch
+        uint64_t *dst = by_read == ha.p ? hb.p : nullptr;
+        if (!dst) { KG_ALLOC(ctx, hc, n_hits); dst = hc.p; }
+        KG_TRY((device_scan<uint32_t>(ctx, n_hits, FirstInReadFlag{by_read, info.p + 4}, CompactKeysU64{by_read, dst}, d_cnt.p)));
+        uint32_t too_long = 0;
+        KG_TRY(read_back(ctx, info.p + 4, &too_long, 1));
+        if (!too_long) {
+            KG_TRY(read_back(ctx, d_cnt.p, &n_uniq, 1));
+            grouped = true;
+            other = dst;
+        }
+    }
+    if (!grouped) {
+        int np = plan_radix_passes(0, bn, 32, 32 + bits_for(h_info[0]), passes);
+        KG_TRY(radix_sort_u64(ctx, ha.p, hb.p, n_hits, passes, np, &sorted));
+        other = sorted == ha.p ? hb.p : ha.p;
+        KG_TRY((device_scan<uint32_t>(ctx, n_hits, HeadFlagU64{sorted}, CompactKeysU64{sorted, other}, d_cnt.p)));
+        KG_TRY(read_back(ctx, d_cnt.p, &n_uniq, 1));
+    }
+    const uint64_t *hits = other;  // unique hits grouped by read (sorted when the general path ran), n_uniq of them
     st->n_unique_hits = n_uniq;
 
     // 2. reads with >= 2 unitigs -> segments; pairs per segment -> offsets

@@ -95,6 +95,33 @@ def test_hits_to_scores_vs_oracle(ctx, oracle_mod, seed, n, n_pairs):
             check_corea(oracle_mod, g.corea(mode), core, deg, mode)
 
 
+@pytest.mark.parametrize("order", ["two_runs", "one_run", "shuffled", "two_runs_sort_forced", "long_read_in_order"])
+def test_hit_orders_take_the_same_result(ctx, oracle_mod, monkeypatch, order):
+    """The build merges the mate files when the reads come in file order (one or two runs of non-decreasing
+    keys) and sorts otherwise, or when a read is too long for the look-back dedup: every route must give the
+    reference's sets."""
+    n, n_pairs = 20000, 150000
+    m1, m2 = synth.metagenome_hits(n, n_pairs, seed=9)
+    rk = np.concatenate([m1.read_key, m2.read_key])
+    ut = np.concatenate([m1.unitig, m2.unitig])
+    if order == "one_run":
+        o = np.argsort(rk, kind="stable"); rk, ut = rk[o], ut[o]
+    elif order == "shuffled":
+        o = np.random.default_rng(1).permutation(rk.shape[0]); rk, ut = rk[o], ut[o]
+    elif order == "two_runs_sort_forced":
+        monkeypatch.setenv("KOMBGPU_NO_MERGE", "1")
+    elif order == "long_read_in_order":   # read 77 gets 300 more hits (with repeats) in mate file 1, in place
+        at = int(np.searchsorted(m1.read_key, 77))
+        extra = np.random.default_rng(2).integers(0, 500, 300).astype(np.uint32)
+        rk = np.concatenate([m1.read_key[:at], np.full(300, 77, np.uint32), m1.read_key[at:], m2.read_key])
+        ut = np.concatenate([m1.unitig[:at], extra, m1.unitig[at:], m2.unitig])
+    exp_edges, exp_p, exp_s = oracle_mod.build_edges(rk, ut)
+    with ctx.build_graph(rk, ut, n) as g:
+        check_graph_against_oracle(oracle_mod, g, n, exp_edges)
+        st = g.stats()
+        assert (st["n_unique_hits"], st["n_pairs"]) == (exp_s, exp_p)
+
+
 def test_repeat_heavy_reads(ctx, oracle_mod):
     """A few reads with hundreds of hits (bwa -a on repeats): quadratic pair blow-up."""
     rng = np.random.default_rng(3)
@@ -129,6 +156,33 @@ def test_deep_core_ramp(ctx, oracle_mod):
         st = g.stats()
         assert core.max() == levels == st["max_coreness"]
         assert st["peel_levels"] == len(set(core.tolist()))
+
+
+@pytest.mark.parametrize("mode", ["warp", "cta"])
+def test_peel_modes_hubs_and_wide_frontiers(ctx, oracle_mod, monkeypatch, mode):
+    """Both process-phase variants of the peel kernel (KOMBGPU_PEEL_MODE) on shapes that exercise every task kind:
+    hub rows above the pool-slice threshold (4096 edges), rows between the warp piece size and that threshold,
+    a level-1 frontier wider than the statically dealt part, and a dense core behind long cascades."""
+    monkeypatch.setenv("KOMBGPU_PEEL_MODE", mode)
+    rng = np.random.default_rng(3)
+    n = 400_000
+    us, vs = [], []
+    # two hubs with 150k and 9k leaves (coreness 1 leaves: one wide frontier), hubs tied into a clique
+    us.append(np.zeros(150_000, np.uint32)); vs.append(np.arange(1000, 151_000, dtype=np.uint32))
+    us.append(np.ones(9_000, np.uint32)); vs.append(np.arange(200_000, 209_000, dtype=np.uint32))
+    iu, iv = np.triu_indices(60, k=1)
+    us.append(iu.astype(np.uint32)); vs.append(iv.astype(np.uint32))          # K_60 on vertices 0..59
+    # mid-size rows: 300 vertices with ~600 random neighbours each among 60..20000
+    for c in range(300, 600):
+        nb = rng.choice(np.arange(600, 20_000), size=600, replace=False).astype(np.uint32)
+        us.append(np.full(600, c, np.uint32)); vs.append(nb)
+    # sparse background
+    us.append(rng.integers(0, n, 600_000).astype(np.uint32)); vs.append(rng.integers(0, n, 600_000).astype(np.uint32))
+    u, v = np.concatenate(us), np.concatenate(vs)
+    exp_edges = oracle_mod.simplify(u, v)
+    with ctx.graph_from_edges(u, v, n) as g:
+        deg, core = check_graph_against_oracle(oracle_mod, g, n, exp_edges)
+        assert deg.max() > 100_000 and core.max() >= 59
 
 
 def test_kats_and_edge_cases(ctx, oracle_mod):
