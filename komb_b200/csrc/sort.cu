@@ -1,9 +1,16 @@
-// sort.cu — stable LSD radix sort of 64-bit keys (hits, unitig pairs, CORE-A
-// rank keys).  Integer, HBM-bound: per pass the keys are read twice (digit
-// histogram, scatter) and written once; the scatter stages a tile in shared
-// memory in digit order so global stores are contiguous runs.  A single-read
-// "onesweep" variant (decoupled look-back) was measured and was not faster here:
-// with ~300 tiles in flight the look-back chains cost what the histogram pass costs.
+// sort.cu — stable LSD radix sort of 64-bit keys (unitig pairs, swapped edges, CORE-A rank keys, and hits
+// when they do not arrive in read order).  Integer, HBM-bound.
+//
+// Default: single-read passes (radix_sweep_kernel, "onesweep"): one kernel histograms every pass's digit up
+// front, then each pass reads the keys once and writes them once; tiles learn their global offsets by a
+// decoupled look-back over per-tile status words.  The tile is staged in shared memory in digit order so
+// global stores are contiguous runs.  Measured on B200 (tools/sort_probe.py): 2.0 TB/s read+write per pass on
+// 33 M keys, 2.1 TB/s on 540 M, against 1.7 / 1.9 TB/s for the three-kernel passes (per-tile histogram, table
+// scan, scatter) that are kept for arrays of 2^30 keys and more and for A/B runs (KOMBGPU_SORT=legacy).
+// What bounds a pass is instruction issue, not DRAM: ~130 thread-instructions per key, half of them the
+// ballot-per-digit-bit ranking (ncu: issue slots 50 % busy, ALU pipe 49 %, barrier stalls 44 % of samples, DRAM
+// 25 % of peak; profiles/r1/r1o_sweep_*).  MATCH.ANY ranks a key in one instruction but runs on the ADU pipe
+// and made every mix of the two slower (KOMBGPU_SORT_MATCH, measured 0/2/4/8 items).
 #include <cstdlib>
 
 #include "primitives.cuh"
@@ -217,52 +224,72 @@ __global__ void __launch_bounds__(kRadix) radix_hist_scan_kernel(uint32_t *hist)
     h[threadIdx.x] = ex;
 }
 
+// tile geometry of the sweep kernel.  Measured on the 33 M-key shape: 512 x 16 keys 1.58 ms per 6-pass sort,
+// 512 x 8 1.70 ms, 256 x 8 1.82 ms: the per-digit phases (prefix over warps, look-back: 256 threads, the rest of
+// the CTA waits at a barrier) are amortised over more keys.
+constexpr int kSwThreads = 512;
+constexpr int kSwItems = 16;
+constexpr int kSwTile = kSwThreads * kSwItems;
+constexpr int kSwWarps = kSwThreads / 32;
+constexpr int kSwMinBlocks = 2;
+
 struct SweepSmem {
-    uint64_t keys[kRsTile];
-    uint32_t warp_cnt[kRsWarps][kRadix];
+    uint64_t keys[kSwTile];
+    uint32_t warp_cnt[kSwWarps][kRadix];
     uint32_t digit_local[kRadix];   // first slot of digit d inside the staged tile
     uint32_t digit_global[kRadix];  // global position of that slot minus digit_local
     uint32_t scan_tmp[kRadix / 32 + 1];
     uint32_t tile;
 };
 
-__global__ void __launch_bounds__(kRsThreads, 3) radix_sweep_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
+// kBits: digit width known at compile time (8), or 0 = read it from `mask`.  kMatch: items per thread ranked with
+// MATCH.ANY instead of ballots.  MATCH is one instruction where the ballot way takes ~50, but it runs on the
+// slow ADU pipe; ranking a few of the 8 items with it spreads the work over both pipes.
+template <int kBits, int kMatch>
+__global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
                                                                     uint64_t n, int shift, uint32_t mask,
                                                                     const uint32_t *__restrict__ digit_base,  // exclusive global histogram of this pass
                                                                     uint32_t *status, uint32_t *tile_counter) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SweepSmem &s = *reinterpret_cast<SweepSmem *>(s_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (kBits) mask = (1u << kBits) - 1u;
     if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
-    for (int i = threadIdx.x; i < kRsWarps * kRadix; i += kRsThreads) (&s.warp_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kSwWarps * kRadix; i += kSwThreads) (&s.warp_cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
-    const uint64_t tile_base = (uint64_t)tile * kRsTile;
-    const uint32_t tile_count = (uint32_t)min((uint64_t)kRsTile, n - tile_base);
+    const uint64_t tile_base = (uint64_t)tile * kSwTile;
+    const uint32_t tile_count = (uint32_t)min((uint64_t)kSwTile, n - tile_base);
 
     // warp-striped load: item j of lane l is tile element warp*256 + j*32 + l, so (warp, j, lane) order is memory
     // order and the sort stays stable
-    uint64_t key[kRsItems];
-    uint16_t rank[kRsItems];
-    const uint32_t warp_base = warp * (32 * kRsItems);
+    uint64_t key[kSwItems];
+    uint16_t rank[kSwItems];
+    const uint32_t warp_base = warp * (32 * kSwItems);
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
+    for (int j = 0; j < kSwItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         key[j] = e < tile_count ? in[tile_base + e] : 0;
     }
-    // rank inside the warp: lanes with the same digit are found with one ballot per digit bit; the group's
-    // leader takes the digit's running count with a shared-memory atomic (issued in j order: stable)
+    // rank inside the warp: lanes with the same digit are found with one ballot per digit bit (or one MATCH); the
+    // group's leader takes the digit's running count with a shared-memory atomic (issued in j order: stable)
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
+    for (int j = 0; j < kSwItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         const bool valid = e < tile_count;
         const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : 0u;
-        uint32_t same = __ballot_sync(kFullMask, valid);
+        uint32_t same;
+        if (j < kMatch) {
+            same = __match_any_sync(kFullMask, valid ? d : 0xffffffffu);   // invalid lanes (tail of the last tile) group apart
+        } else {
+            same = __ballot_sync(kFullMask, valid);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            if ((mask >> b) == 0) break;  // uniform: digits narrower than 8 bits need fewer ballots
-            const uint32_t vote = __ballot_sync(kFullMask, (d >> b) & 1u);
-            same &= ((d >> b) & 1u) ? vote : ~vote;
+            for (int b = 0; b < 8; ++b) {
+                if (kBits ? (b >= kBits) : ((mask >> b) == 0)) break;  // uniform: narrower digits need fewer ballots
+                const uint32_t bit = (d >> b) & 1u;
+                const uint32_t vote = __ballot_sync(kFullMask, bit);
+                same &= vote ^ (bit - 1u);   // lanes whose bit equals mine
+            }
         }
         const uint32_t lead = valid ? (uint32_t)__ffs(same) - 1u : lane;
         uint32_t base = 0;
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) radix_sweep_kernel(const uint64
     uint32_t digit_total = 0;
     const bool digit_thread = threadIdx.x < kRadix;
     if (digit_thread) {
-        for (int w = 0; w < kRsWarps; ++w) {
+        for (int w = 0; w < kSwWarps; ++w) {
             const uint32_t c = s.warp_cnt[w][threadIdx.x];
             s.warp_cnt[w][threadIdx.x] = digit_total;
             digit_total += c;
@@ -302,7 +329,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) radix_sweep_kernel(const uint64
 
     // stage the tile in digit order (the look-back of the digit threads follows, overlapping other CTAs' work)
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
+    for (int j = 0; j < kSwItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         if (e < tile_count) {
             const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) radix_sweep_kernel(const uint64
     __syncthreads();
 
     // contiguous runs out to global memory
-    for (uint32_t i = threadIdx.x; i < tile_count; i += kRsThreads) {
+    for (uint32_t i = threadIdx.x; i < tile_count; i += kSwThreads) {
         const uint64_t k = s.keys[i];
         const uint32_t d = (uint32_t)(k >> shift) & mask;
         out[(uint64_t)(s.digit_global[d] + i)] = k;
@@ -370,12 +397,19 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
     static bool attr_set = false;
     if (!attr_set) {
         KG_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-        KG_CUDA(ctx, cudaFuncSetAttribute(radix_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+#define KG_SWEEP_ATTR(BITS, MATCH) \
+    KG_CUDA(ctx, cudaFuncSetAttribute(radix_sweep_kernel<BITS, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)))
+        KG_SWEEP_ATTR(8, 8); KG_SWEEP_ATTR(0, 8); KG_SWEEP_ATTR(8, 4); KG_SWEEP_ATTR(0, 4);
+        KG_SWEEP_ATTR(8, 2); KG_SWEEP_ATTR(0, 2); KG_SWEEP_ATTR(8, 0); KG_SWEEP_ATTR(0, 0);
+#undef KG_SWEEP_ATTR
         attr_set = true;
     }
     const uint32_t n_tiles = ceil_div_u64(n, kRsTile);
     uint64_t *src = a, *dst = b;
+    const char *match_env = getenv("KOMBGPU_SORT_MATCH");   // items per thread ranked with MATCH.ANY (0, 2, 4, 8)
+    const int n_match = match_env ? atoi(match_env) : 0;
     if (!legacy) {
+        const uint32_t n_tiles = ceil_div_u64(n, kSwTile);
         // [n_passes x 256 digit histograms | n_passes tile counters | n_passes x n_tiles x 256 status words]
         const size_t head = (size_t)n_passes * kRadix + kMaxPasses;
         DevBuf<uint32_t> ws;
@@ -388,8 +422,16 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
         KG_LAUNCH(ctx, radix_global_hist_kernel, hist_grid, kRsThreads, 0, src, n, pl, ws.p);
         KG_LAUNCH(ctx, radix_hist_scan_kernel, n_passes, kRadix, 0, ws.p);
         for (int p = 0; p < n_passes; ++p) {
-            KG_LAUNCH(ctx, radix_sweep_kernel, n_tiles, kRsThreads, sizeof(SweepSmem), src, dst, n, pl.shift[p], pl.mask[p],
-                      ws.p + (size_t)p * kRadix, ws.p + head + (size_t)p * n_tiles * kRadix, ws.p + (size_t)n_passes * kRadix + p);
+            const uint32_t *dbase = ws.p + (size_t)p * kRadix;
+            uint32_t *status = ws.p + head + (size_t)p * n_tiles * kRadix, *counter = ws.p + (size_t)n_passes * kRadix + p;
+#define KG_SWEEP(BITS, MATCH)                                                                                        \
+    KG_LAUNCH(ctx, (radix_sweep_kernel<BITS, MATCH>), n_tiles, kSwThreads, sizeof(SweepSmem), src, dst, n, pl.shift[p], \
+              pl.mask[p], dbase, status, counter)
+            if (n_match == 8) { if (passes[p].bits == 8) KG_SWEEP(8, 8); else KG_SWEEP(0, 8); }
+            else if (n_match == 4) { if (passes[p].bits == 8) KG_SWEEP(8, 4); else KG_SWEEP(0, 4); }
+            else if (n_match == 2) { if (passes[p].bits == 8) KG_SWEEP(8, 2); else KG_SWEEP(0, 2); }
+            else { if (passes[p].bits == 8) KG_SWEEP(8, 0); else KG_SWEEP(0, 0); }
+#undef KG_SWEEP
             uint64_t *t = src; src = dst; dst = t;
         }
         *sorted = src;
