@@ -16,8 +16,10 @@ from komb_b200 import synth
 VARIANTS = [
     ("cta", {"KOMBGPU_PEEL_MODE": "cta"}),
     ("warp", {"KOMBGPU_PEEL_MODE": "warp"}),
-    ("warp keep4", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "4"}),
-    ("warp wsplit256", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_WSPLIT": "256"}),
+    ("warp park20", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "20"}),
+    ("warp park50", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "50"}),
+    ("warp park100", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "100"}),
+    ("warp park200", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "200"}),
 ]
 KNOBS = ["KOMBGPU_PEEL_MODE", "KOMBGPU_PEEL_KEEP", "KOMBGPU_PEEL_PARK", "KOMBGPU_PEEL_WSPLIT", "KOMBGPU_PEEL_UNROLL"]
 
