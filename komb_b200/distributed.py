@@ -110,8 +110,18 @@ class Comm:
             import torch
             sizes = [int(x) for x in self.all_gather_ints([arr.numel()])[:, 0]]
             out = torch.empty(sum(sizes), dtype=arr.dtype, device=arr.device)
+            mx = max(sizes)
             if len(set(sizes)) == 1:
                 self.dist.all_gather_into_tensor(out, arr.contiguous())
+            elif sum(sizes) * arr.element_size() >= (8 << 20) and mx * self.world <= 1.25 * sum(sizes):
+                # large, nearly even segments (the CSR of a balanced range partition): ONE all-gather of pieces
+                # padded to the longest (NCCL's ring / NVLS path), then one device copy that drops the padding.
+                # The list form below turns into one broadcast per rank, which ran at a third of that bandwidth.
+                pad = torch.empty(self.world * mx, dtype=arr.dtype, device=arr.device)
+                src = pad[self.rank * mx:(self.rank + 1) * mx]      # in place: my slot of the padded buffer
+                src[:arr.numel()].copy_(arr)
+                self.dist.all_gather_into_tensor(pad, src)
+                torch.cat([pad[j * mx:j * mx + sizes[j]] for j in range(self.world)], out=out)
             else:
                 # uneven segments: every rank's piece lands at its final offset, no padding and no second copy
                 offs = np.concatenate([[0], np.cumsum(sizes)])
