@@ -182,6 +182,16 @@ int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode);
 int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t *v, int32_t *degree,
                           int32_t *coreness, double *score);
 
+/* Densest k-core (needs kombgpu_coreness): the level k* whose core {v : coreness(v) >= k*} maximises
+ * edges / vertices, with that block's size.  Bulk analogue of the greedy densest-block peel the reference keeps,
+ * unreachable from main, in CombineCoreA::runMerge over HashIndexedMinHeap (src/CombineCoreA.h:45-219,
+ * src/HashIndexedMinHeap.h:10-238) for suspiciousness == nullptr: same density (2E directed entries over 2V row
+ * and column nodes), blocks restricted to the nested k-cores (still a 2-approximation of the densest subgraph),
+ * ties to the largest block.  The reference's own result depends on heap tie order and uninitialised memory, so
+ * there is no parity obligation. */
+int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uint32_t *n_vertices, uint64_t *n_edges,
+                               double *density);
+
 int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out);
 
 /* Device pointers of the graph's arrays (valid until kombgpu_graph_destroy);

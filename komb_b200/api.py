@@ -233,6 +233,12 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_summary(self._h, byref(mc), byref(ms)))
         return mc.value, ms.value
 
+    def densest_core(self) -> dict:
+        """Densest k-core {v : coreness(v) >= k}: level, size and edges / vertices (kombgpu_graph_densest_core)."""
+        k, nv, ne, d = c_int32(), c_uint32(), c_uint64(), c_double()
+        self._ctx._check(self._lib.kombgpu_graph_densest_core(self._h, byref(k), byref(nv), byref(ne), byref(d)))
+        return {"k": k.value, "n_vertices": nv.value, "n_edges": ne.value, "density": d.value}
+
     def stats(self) -> dict:
         st = Stats()
         self._ctx._check(self._lib.kombgpu_graph_stats(self._h, byref(st)))

@@ -150,6 +150,30 @@ def corea_ranks(core: np.ndarray, deg: np.ndarray, key_mode: int = KEY_REF32):
     return rd, rk
 
 
+def densest_core(core: np.ndarray, edges: np.ndarray) -> dict:
+    """Checker for kombgpu_graph_densest_core: the k-core maximising edges / vertices (equal density: the larger
+    block; k = smallest coreness inside the block).
+    Restates the density bookkeeping of CombineCoreA::runMerge (src/CombineCoreA.h:112-145: suspiciousSum /
+    numOfNodesBelong with suspiciousness == nullptr) over the nested k-cores instead of single-node removals."""
+    n = int(core.shape[0])
+    if n == 0 or edges.shape[0] == 0:
+        return {"k": 0, "n_vertices": n, "n_edges": int(edges.shape[0]), "density": (edges.shape[0] / n) if n else 0.0}
+    u, v = unpack_edges(edges)
+    kmax = int(core.max())
+    hv = np.bincount(core, minlength=kmax + 1).astype(np.int64)
+    he = np.bincount(np.minimum(core[u], core[v]), minlength=kmax + 1).astype(np.int64)
+    vk = np.cumsum(hv[::-1])[::-1]
+    ek = np.cumsum(he[::-1])[::-1]
+    best = None
+    for k in range(kmax, -1, -1):
+        if vk[k] == 0:
+            continue
+        d = float(ek[k]) / float(vk[k])
+        if best is None or d > best["density"] or (d == best["density"] and int(vk[k]) > best["n_vertices"]):
+            best = {"k": k, "n_vertices": int(vk[k]), "n_edges": int(ek[k]), "density": d}
+    return best
+
+
 def unpack_edges(packed: np.ndarray):
     return (packed >> np.uint64(32)).astype(np.uint32), (packed & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 

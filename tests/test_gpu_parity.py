@@ -185,6 +185,49 @@ def test_peel_modes_hubs_and_wide_frontiers(ctx, oracle_mod, monkeypatch, mode):
         assert deg.max() > 100_000 and core.max() >= 59
 
 
+def test_cfg2_full_size(ctx, oracle_mod):
+    """BASELINE.json config 2 at its full size (1 M unitigs, 5 M read pairs, ~20 M hits): edge list, degree and
+    coreness bit-exact against the CPU oracle, CORE-A within tolerance in both key modes."""
+    n = 1_000_000
+    m1, m2 = synth.metagenome_hits(n, 5_000_000, seed=11)
+    rk = np.concatenate([m1.read_key, m2.read_key])
+    ut = np.concatenate([m1.unitig, m2.unitig])
+    exp_edges, exp_p, exp_s = oracle_mod.build_edges(rk, ut)
+    exp_deg, exp_core = oracle_mod.coreness(n, exp_edges)
+    with ctx.build_graph(rk, ut, n) as g:
+        u, v = g.edges()
+        assert np.array_equal(oracle_mod.pack_edges(u, v), exp_edges)
+        assert np.array_equal(g.degree(), exp_deg) and np.array_equal(g.coreness(), exp_core)
+        st = g.stats()
+        assert (st["n_unique_hits"], st["n_pairs"], st["n_edges"]) == (exp_s, exp_p, exp_edges.shape[0])
+        for mode in (oracle_mod.KEY_REF32, oracle_mod.KEY_EXACT64):
+            check_corea(oracle_mod, g.corea(mode), exp_core, exp_deg, mode)
+        assert g.densest_core() == oracle_mod.densest_core(exp_core, exp_edges)
+
+
+def test_densest_core(ctx, oracle_mod):
+    """kombgpu_graph_densest_core against the numpy checker, plus known answers: a K_40 planted in a sparse graph is
+    the densest core (density 19.5 = C(40,2)/40); an empty graph gives level 0."""
+    rng = np.random.default_rng(5)
+    n = 30_000
+    iu, iv = np.triu_indices(40, k=1)
+    u = np.concatenate([iu + 100, rng.integers(0, n, 90_000)]).astype(np.uint32)
+    v = np.concatenate([iv + 100, rng.integers(0, n, 90_000)]).astype(np.uint32)
+    exp_edges = oracle_mod.simplify(u, v)
+    with ctx.graph_from_edges(u, v, n) as g:
+        core = g.coreness()
+        got = g.densest_core()
+        assert got == oracle_mod.densest_core(core, exp_edges)
+        assert got["k"] == 39 and got["n_vertices"] == 40 and got["n_edges"] == 780 and got["density"] == 19.5
+    us, vs = synth.rmat_edges(16, 600_000, n_vertices=50_000, seed=3)
+    exp_edges = oracle_mod.simplify(us, vs)
+    with ctx.graph_from_edges(us, vs, 50_000) as g:
+        assert g.densest_core() == oracle_mod.densest_core(g.coreness(), exp_edges)
+    with ctx.graph_from_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 7) as g:
+        g.coreness()
+        assert g.densest_core() == {"k": 0, "n_vertices": 7, "n_edges": 0, "density": 0.0}
+
+
 def test_kats_and_edge_cases(ctx, oracle_mod):
     def run(n, pairs):
         u = np.array([p[0] for p in pairs], np.uint32)

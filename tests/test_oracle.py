@@ -100,3 +100,18 @@ def test_build_edges_semantics(oracle_mod):
     assert (P, S) == (4, 6)
     e0, p0, s0 = oracle_mod.build_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32))
     assert e0.shape[0] == 0 and p0 == 0 and s0 == 0
+
+
+def test_densest_core_checker_known_answers(oracle_mod):
+    """oracle.densest_core (checker of kombgpu_graph_densest_core): K_6 plus a pendant path -> the 5-core K_6,
+    density C(6,2)/6 = 2.5 (the empty levels 2..4 name the same block: k is the block's smallest coreness); a
+    ring is its own densest core (density 1)."""
+    k6 = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+    pairs = k6 + [(5, 6), (6, 7), (7, 8)]
+    u = np.array([p[0] for p in pairs], np.uint32); v = np.array([p[1] for p in pairs], np.uint32)
+    edges = oracle_mod.simplify(u, v)
+    _, core = oracle_mod.coreness(9, edges)
+    assert oracle_mod.densest_core(core, edges) == {"k": 5, "n_vertices": 6, "n_edges": 15, "density": 2.5}
+    ring = oracle_mod.simplify(np.arange(8, dtype=np.uint32), ((np.arange(8) + 1) % 8).astype(np.uint32))
+    _, core = oracle_mod.coreness(8, ring)
+    assert oracle_mod.densest_core(core, ring) == {"k": 2, "n_vertices": 8, "n_edges": 8, "density": 1.0}
