@@ -16,10 +16,8 @@ from komb_b200 import synth
 VARIANTS = [
     ("cta", {"KOMBGPU_PEEL_MODE": "cta"}),
     ("warp", {"KOMBGPU_PEEL_MODE": "warp"}),
-    ("warp park20", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "20"}),
-    ("warp park50", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "50"}),
-    ("warp park100", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "100"}),
-    ("warp park200", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_PARK": "200"}),
+    ("warp keep4", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "4"}),
+    ("warp keep32", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "32"}),
 ]
 KNOBS = ["KOMBGPU_PEEL_MODE", "KOMBGPU_PEEL_KEEP", "KOMBGPU_PEEL_PARK", "KOMBGPU_PEEL_WSPLIT", "KOMBGPU_PEEL_UNROLL"]
 
@@ -28,6 +26,10 @@ def make_graph(ctx, w):
     if w == "cfg2":
         m1, m2 = synth.metagenome_hits(1_000_000, 5_000_000, seed=11)
         return ctx.build_graph(np.concatenate([m1.read_key, m2.read_key]), np.concatenate([m1.unitig, m2.unitig]), 1_000_000)
+    if w == "path":      # one chain: the peel's latency per dependent step, nothing else (two waves meet in the middle)
+        n = 200_000
+        u = np.arange(n - 1, dtype=np.uint32)
+        return ctx.graph_from_edges(u, u + 1, n)
     if w == "ramp":
         u, v = synth.ramp_edges(1500, 20)
         return ctx.graph_from_edges(u, v, 1500 * 20)
