@@ -192,9 +192,11 @@ int peel_coreness(kombgpu_graph *g) {
     init.tune[0] = (uint32_t)kRingKeep;
     init.tune[1] = kWarpSplit;
     init.tune[2] = 0;
+    init.tune[3] = kThinEdges;
     if (const char *e = getenv("KOMBGPU_PEEL_KEEP")) init.tune[0] = (uint32_t)atoi(e);
     if (const char *e = getenv("KOMBGPU_PEEL_WSPLIT")) init.tune[1] = (uint32_t)atoi(e) < kWarpSplitMin ? kWarpSplitMin : (uint32_t)atoi(e);
     if (const char *e = getenv("KOMBGPU_PEEL_PARK")) init.tune[2] = (uint32_t)atoi(e);
+    if (const char *e = getenv("KOMBGPU_PEEL_THIN")) init.tune[3] = (uint32_t)atoi(e);
     DevBuf<unsigned long long> trace;
     const char *trace_path = getenv("KOMBGPU_TRACE");
     const uint32_t trace_cap = 1u << 16;

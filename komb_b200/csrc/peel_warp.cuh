@@ -45,6 +45,7 @@ struct WarpTune {
     int32_t keep;      // queued ring tickets above which discoveries are shared through the pool
     uint32_t wsplit;   // edges of a row one warp keeps
     uint32_t park_ns;  // sleep between two polls of a parked warp (0 = spin)
+    uint32_t thin;     // a batch up to this many edges may hand its discoveries on in registers
 };
 
 struct WarpShared {
@@ -83,6 +84,7 @@ __device__ __forceinline__ void ring_put(WarpShared &sh, uint32_t ticket, uint64
 // hand-off, a parked warp's wake-up and the 32-row bookkeeping (2.2 us per step measured on a path graph, of
 // which the three memory round trips are 0.45 us).
 constexpr uint32_t kCarry = 2;
+constexpr uint32_t kThinEdges = 512;   // a batch up to this size may hand its discoveries on in registers
 template <bool kDist, int kU>
 __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const uint32_t m, const int32_t k,
                                                const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, int32_t *deg,
@@ -176,7 +178,10 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const uint32_
         total = __shfl_sync(kFullMask, incl, 31);
     }
     const uint32_t row_lo = (uint32_t)my_row, row_hi = (uint32_t)(my_row >> 32);
-    const bool direct = total <= 32u * kU;
+    // latency-bound batches decrement without looking first: one iteration's worth of edges, or the (<= 2 row)
+    // batch of a cascade being followed, whose rows may be a few hundred entries long
+    const bool thin = total <= tn.thin;
+    const bool direct = total <= 32u * kU || (m <= kCarry && thin);
     // binary search over the rows of the batch: log2 steps for m rows (none for one row)
     const uint32_t top = m <= 1 ? 0u : (1u << (31 - __clz((int)(m - 1))));
 
@@ -238,21 +243,20 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const uint32_
         for (int t = 0; t < kU; ++t) c += push[t] ? 1u : 0u;
         const uint32_t any = __ballot_sync(kFullMask, c != 0);
         if (any == 0) continue;
-        if (direct && (uint32_t)__popc(any) <= kCarry && __ballot_sync(kFullMask, c > 1) == 0) {
+        if (thin && n_carry + (uint32_t)__popc(any) <= kCarry && __ballot_sync(kFullMask, c > 1) == 0) {
             // a thin cascade: keep the discoveries in registers, they are this warp's next batch
             uint32_t val = 0;
 #pragma unroll
             for (int t = 0; t < kU; ++t) if (push[t]) val = u[t];
-            n_carry = (uint32_t)__popc(any);
             uint32_t left = any;
-            carry = kEmpty;
 #pragma unroll
-            for (uint32_t i = 0; i < kCarry; ++i) {   // the i-th discovery goes to lane i
+            for (uint32_t i = 0; i < kCarry; ++i) {   // the i-th discovery of this iteration goes to lane n_carry + i
                 const uint32_t vi = __shfl_sync(kFullMask, val, left ? __ffs(left) - 1 : 0);
-                if (lane == i && left) carry = (uint64_t)vi;
+                if (lane == n_carry + i && left) carry = (uint64_t)vi;
                 left &= left - 1;
             }
-            continue;   // `direct`: this was the only iteration
+            n_carry += (uint32_t)__popc(any);
+            continue;
         }
         const uint32_t inc = warp_incl_scan_add(c);
         const uint32_t tot = __shfl_sync(kFullMask, inc, 31);
@@ -439,6 +443,7 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
     tn.keep = (int32_t)st->tune[0];
     tn.wsplit = st->tune[1];
     tn.park_ns = st->tune[2];
+    tn.thin = st->tune[3];
     uint32_t rb = 0, re = 0;   // ring tickets this warp owns
     uint32_t removed = 0, n_shared = 0, batches = 0;
     uint32_t spins = 0;

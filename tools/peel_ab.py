@@ -16,10 +16,13 @@ from komb_b200 import synth
 VARIANTS = [
     ("cta", {"KOMBGPU_PEEL_MODE": "cta"}),
     ("warp", {"KOMBGPU_PEEL_MODE": "warp"}),
-    ("warp keep4", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "4"}),
-    ("warp keep32", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_KEEP": "32"}),
+    ("warp thin128", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_THIN": "128"}),
+    ("warp thin256", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_THIN": "256"}),
+    ("warp thin1024", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_THIN": "1024"}),
+    ("warp thin4096", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_THIN": "4096"}),
+    ("warp thin1024 wsplit256", {"KOMBGPU_PEEL_MODE": "warp", "KOMBGPU_PEEL_THIN": "1024", "KOMBGPU_PEEL_WSPLIT": "256"}),
 ]
-KNOBS = ["KOMBGPU_PEEL_MODE", "KOMBGPU_PEEL_KEEP", "KOMBGPU_PEEL_PARK", "KOMBGPU_PEEL_WSPLIT", "KOMBGPU_PEEL_UNROLL"]
+KNOBS = ["KOMBGPU_PEEL_MODE", "KOMBGPU_PEEL_KEEP", "KOMBGPU_PEEL_PARK", "KOMBGPU_PEEL_WSPLIT", "KOMBGPU_PEEL_UNROLL", "KOMBGPU_PEEL_THIN"]
 
 
 def make_graph(ctx, w):
