@@ -225,9 +225,8 @@ def run_ours(args):
     def step_e2e():
         """The call a user of the C ABI makes: host hits in (page-locked), every output the
         komb2 host writes to its three files back on the host (page-locked)."""
-        g = ctx.build_graph(rk_h.numpy().view(np.uint32), ut_h.numpy().view(np.uint32), N_UNITIGS)
-        r = g.results(komb_b200.KEY_REF32, out={"u": pin["u"], "v": pin["v"], "degree": pin["deg"], "coreness": pin["core"],
-                                                "score": pin["score"]})
+        g, r = ctx.analyse_hits(rk_h.numpy().view(np.uint32), ut_h.numpy().view(np.uint32), N_UNITIGS, komb_b200.KEY_REF32,
+                                out={"u": pin["u"], "v": pin["v"], "degree": pin["deg"], "coreness": pin["core"], "score": pin["score"]})
         st = g.stats()
         g.close()
         return st, sum(a.nbytes for a in r.values())

@@ -192,6 +192,17 @@ int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t 
 int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uint32_t *n_vertices, uint64_t *n_edges,
                                double *density);
 
+/* The whole path in one call, host buffers in and out: what komb2 does between readSAM and its three writers
+ * (getEdgeInfo ... anomalyDetection, src/komb2.cpp:104-132).  Same results as kombgpu_build_graph followed by
+ * kombgpu_graph_results; the difference is scheduling: the edge list is final half-way through the build (the CSR
+ * only indexes it), so its download starts there and runs under the rest of the build, the peel and CORE-A.
+ * u / v (both or neither) must hold edge_capacity entries; more edges than that is KOMBGPU_EINVAL (build with
+ * kombgpu_build_graph and size the buffers from kombgpu_graph_counts instead).  Any output pointer may be NULL.
+ * On success *out owns the device graph (kombgpu_graph_destroy). */
+int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                         uint32_t n_vertices, int key_mode, uint64_t edge_capacity, uint32_t *u, uint32_t *v,
+                         int32_t *degree, int32_t *coreness, double *score, kombgpu_graph **out);
+
 int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out);
 
 /* Device pointers of the graph's arrays (valid until kombgpu_graph_destroy);

@@ -59,6 +59,8 @@ SIGNATURES = {
     "kombgpu_corea": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p]),
     "kombgpu_graph_corea": (c_int, [c_void_p, c_int, c_void_p]),
     "kombgpu_graph_summary": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_double)]),
+    "kombgpu_analyse_hits": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, POINTER(c_void_p)]),
     "kombgpu_graph_densest_core": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint64), POINTER(c_double)]),
     "kombgpu_graph_analyse": (c_int, [c_void_p, c_int]),
     "kombgpu_graph_results": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

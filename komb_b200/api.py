@@ -114,6 +114,33 @@ class Context:
         return self._pair_call(self._lib.kombgpu_build_graph, self._lib.kombgpu_build_graph_dev,
                                read_key, unitig, int(n_vertices))
 
+    def analyse_hits(self, read_key, unitig, n_vertices: int, key_mode: int = KEY_REF32, out: dict | None = None,
+                     edge_capacity: int | None = None) -> tuple["Graph", dict]:
+        """Host hits in, every result on the host, one call (kombgpu_analyse_hits): the edge list starts downloading
+        half-way through the build.  `out` may hold caller buffers (u, v, degree, coreness, score; e.g. pinned_empty
+        arrays); u / v must hold `edge_capacity` entries (default: their length, or 3 x the number of hits when
+        they are allocated here).  Returns the graph and the result arrays (u / v cut to the edge count)."""
+        ha, hb = _host(read_key, np.uint32), _host(unitig, np.uint32)
+        if ha.shape != hb.shape or ha.ndim != 1:
+            raise ValueError("expected two 1-D arrays of equal length")
+        out = out or {}
+        n = int(n_vertices)
+        if out.get("u") is not None:
+            cap = min(out["u"].shape[0], out["v"].shape[0]) if edge_capacity is None else int(edge_capacity)
+            bu, bv = out["u"], out["v"]
+        else:
+            cap = 3 * ha.shape[0] if edge_capacity is None else int(edge_capacity)
+            bu, bv = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        r = {"degree": Graph._out(out.get("degree"), n, np.int32), "coreness": Graph._out(out.get("coreness"), n, np.int32),
+             "score": Graph._out(out.get("score"), n, np.float64)}
+        g = c_void_p()
+        self._check(self._lib.kombgpu_analyse_hits(self._h, _ptr(ha), _ptr(hb), ha.shape[0], n, int(key_mode), cap, _ptr(bu), _ptr(bv),
+                                                   _ptr(r["degree"]), _ptr(r["coreness"]), _ptr(r["score"]), byref(g)))
+        graph = Graph(self, g, None)
+        m = graph.counts()[1]
+        r["u"], r["v"] = bu[:m], bv[:m]
+        return graph, r
+
     def graph_from_edges(self, u, v, n_vertices: int) -> "Graph":
         return self._pair_call(self._lib.kombgpu_graph_from_edges, self._lib.kombgpu_graph_from_edges_dev,
                                u, v, int(n_vertices))

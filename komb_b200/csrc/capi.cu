@@ -7,6 +7,17 @@
 #include "graph.cuh"
 
 namespace kg {
+namespace { __global__ void small_copy_kernel(const unsigned char *__restrict__ src, unsigned char *dst, uint32_t bytes); }
+
+int small_read_back(kombgpu_ctx *ctx, const void *dev, void *host, size_t bytes) {
+    small_copy_kernel<<<1, 256, 0, ctx->stream>>>(static_cast<const unsigned char *>(dev), static_cast<unsigned char *>(ctx->pinned),
+                                                  (uint32_t)bytes);
+    ctx->launches++;
+    KG_CUDA(ctx, cudaPeekAtLastError());
+    KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(host, ctx->pinned, bytes);
+    return KOMBGPU_OK;
+}
 
 static thread_local std::string g_create_error;
 
@@ -113,6 +124,10 @@ int download(kombgpu_ctx *ctx, const T *dev, T *host, size_t count) {
     KG_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KOMBGPU_OK;
+}
+
+__global__ void small_copy_kernel(const unsigned char *__restrict__ src, unsigned char *dst, uint32_t bytes) {
+    for (uint32_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
 }
 
 __global__ void unpack_edges_kernel(const uint64_t *__restrict__ edges, uint64_t n_edges, uint32_t *__restrict__ u,
@@ -452,6 +467,79 @@ int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t 
     cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
     if (rc != KOMBGPU_OK) return rc;
     if (ce != cudaSuccess) return ctx_fail(ctx, KOMBGPU_ECUDA, "results copy stream: %s", cudaGetErrorString(ce));
+    return KOMBGPU_OK;
+}
+
+int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                         int key_mode, uint64_t edge_capacity, uint32_t *u, uint32_t *v, int32_t *degree, int32_t *coreness,
+                         double *score, kombgpu_graph **out) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if (!out || (n_hits && (!read_key || !unitig))) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    if ((u == nullptr) != (v == nullptr)) return ctx_fail(ctx, KOMBGPU_EINVAL, "u and v must be given together");
+    *out = nullptr;
+    if (n_vertices >= 0xfffffffeu) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_vertices too large");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    kombgpu_graph *g = new (std::nothrow) kombgpu_graph();
+    if (!g) return ctx_fail(ctx, KOMBGPU_ENOMEM, "host allocation");
+    g->ctx = ctx;
+    g->st.max_coreness = -1;
+    const uint64_t launches0 = ctx->launches;
+    DevBuf<uint32_t> du, dv;   // unpacked edge list: lives until the copy stream has drained
+    bool copies_in_flight = false;
+    auto fail = [&](int rc) {
+        if (copies_in_flight) cudaStreamSynchronize(ctx->copy_stream);
+        graph_release(g);
+        delete g;
+        return rc;
+    };
+    int rc = KOMBGPU_OK;
+    {
+        StageTimer timer(ctx);
+        DevBuf<uint32_t> da, db;
+        rc = upload(ctx, da, read_key, n_hits);
+        if (rc == KOMBGPU_OK) rc = upload(ctx, db, unitig, n_hits);
+        // stage 1a: the simple edge list (final here: the CSR only adds an index over it)
+        DevBuf<uint64_t> edges;
+        uint64_t E = 0;
+        if (rc == KOMBGPU_OK) rc = hits_to_edges(ctx, da.p, db.p, n_hits, n_vertices, edges, &E, &g->st);
+        if (rc == KOMBGPU_OK && u && E > edge_capacity)
+            rc = ctx_fail(ctx, KOMBGPU_EINVAL, "%llu edges do not fit the caller's edge buffers (%llu)", (unsigned long long)E,
+                          (unsigned long long)edge_capacity);
+        if (rc != KOMBGPU_OK) return fail(rc);
+        // its download starts now, on the copy stream, under the rest of the build, the peel and CORE-A
+        if (u && E) {
+            if (!du.alloc(ctx, E) || !dv.alloc(ctx, E)) return fail(ctx_fail(ctx, KOMBGPU_ENOMEM, "edge list staging"));
+            unpack_edges_kernel<<<min(ceil_div_u64(E, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(edges.p, E, du.p, dv.p);
+            ctx->launches++;
+            cudaEvent_t ready = nullptr;
+            cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(ready, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
+            copies_in_flight = true;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(u, du.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(v, dv.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (ready) cudaEventDestroy(ready);
+            if (e != cudaSuccess) return fail(ctx_fail(ctx, KOMBGPU_ECUDA, "analyse_hits: %s", cudaGetErrorString(e)));
+        }
+        // stage 1b: CSR
+        rc = csr_from_edges(ctx, edges, E, n_vertices, g);
+        g->st.ms_build = timer.stop();
+        if (rc != KOMBGPU_OK) return fail(rc);
+    }
+    g->st.kernel_launches = ctx->launches - launches0;
+    // stages 2 + 3, then the small downloads behind them on the compute stream
+    rc = kombgpu_coreness(g, nullptr);
+    if (rc == KOMBGPU_OK) rc = kombgpu_graph_corea(g, key_mode, nullptr);
+    if (rc == KOMBGPU_OK && degree && g->n) rc = download(ctx, g->deg, degree, g->n);
+    if (rc == KOMBGPU_OK && coreness && g->n) rc = download(ctx, g->core, coreness, g->n);
+    if (rc == KOMBGPU_OK && score && g->n) rc = download(ctx, g->score, score, g->n);
+    if (rc != KOMBGPU_OK) return fail(rc);
+    if (copies_in_flight) {
+        cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+        copies_in_flight = false;
+        if (ce != cudaSuccess) return fail(ctx_fail(ctx, KOMBGPU_ECUDA, "analyse_hits copy stream: %s", cudaGetErrorString(ce)));
+    }
+    *out = g;
     return KOMBGPU_OK;
 }
 

@@ -124,18 +124,20 @@ inline int bits_for(uint64_t max_value) {  // number of bits needed to represent
     return b;
 }
 
-// read back `count` elements of T from the device through pinned staging
+// Small read-backs (counters, totals, the peel's state) go through a copy KERNEL that stores into the context's
+// page-locked staging area (device-accessible under UVA), not through cudaMemcpy: a DMA copy would queue on the
+// device-to-host copy engine behind a bulk download that is in flight on the copy stream (the edge list, 5 ms for
+// cfg2) and stall the compute stream's host for that long.
+int small_read_back(kombgpu_ctx *ctx, const void *dev, void *host, size_t bytes);   // capi.cu; bytes <= ctx->pinned_bytes
+
+// read back `count` elements of T from the device
 template <typename T>
 int read_back(kombgpu_ctx *ctx, const T *dev, T *host, size_t count) {
     size_t bytes = count * sizeof(T);
-    if (bytes <= ctx->pinned_bytes) {
-        KG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        memcpy(host, ctx->pinned, bytes);
-    } else {
-        KG_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (bytes == 0) return KOMBGPU_OK;
+    if (bytes <= ctx->pinned_bytes) return small_read_back(ctx, dev, host, bytes);
+    KG_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    KG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KOMBGPU_OK;
 }
 

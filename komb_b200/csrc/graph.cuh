@@ -40,6 +40,8 @@ int csr_from_directed(kombgpu_ctx *ctx, const uint64_t *entries, uint64_t count,
                       uint32_t n_global, uint64_t **row_ptr_out, uint32_t **col_out, int32_t **deg_out, int32_t *max_deg_out,
                       uint64_t *n_directed_out);
 
+int csr_from_edges(kombgpu_ctx *ctx, DevBuf<uint64_t> &edges, uint64_t n_edges, uint32_t n, kombgpu_graph *g);
+
 int adopt_csr(kombgpu_ctx *ctx, const uint64_t *row_ptr, const uint32_t *col, uint32_t n, kombgpu_graph *g);
 
 // stage 2 (peel.cu)

@@ -205,6 +205,31 @@ def test_cfg2_full_size(ctx, oracle_mod):
         assert g.densest_core() == oracle_mod.densest_core(exp_core, exp_edges)
 
 
+def test_analyse_hits_one_call(ctx, oracle_mod):
+    """kombgpu_analyse_hits (host hits in, all results out, edge download overlapped) gives what the staged calls
+    give; too small edge buffers are an error, not a truncation."""
+    import komb_b200
+    n, n_pairs = 30000, 250000
+    m1, m2 = synth.metagenome_hits(n, n_pairs, seed=4)
+    rk = np.concatenate([m1.read_key, m2.read_key])
+    ut = np.concatenate([m1.unitig, m2.unitig])
+    exp_edges, _, _ = oracle_mod.build_edges(rk, ut)
+    exp_deg, exp_core = oracle_mod.coreness(n, exp_edges)
+    pin = {"u": ctx.pinned_empty(exp_edges.shape[0] + 10, np.uint32), "v": ctx.pinned_empty(exp_edges.shape[0] + 10, np.uint32)}
+    for out in (None, pin):
+        g, r = ctx.analyse_hits(rk, ut, n, oracle_mod.KEY_REF32, out=out)
+        with g:
+            assert np.array_equal(oracle_mod.pack_edges(r["u"], r["v"]), exp_edges)
+            assert np.array_equal(r["degree"], exp_deg) and np.array_equal(r["coreness"], exp_core)
+            check_corea(oracle_mod, r["score"], exp_core, exp_deg, oracle_mod.KEY_REF32)
+            assert g.stats()["n_edges"] == exp_edges.shape[0]
+    with pytest.raises(komb_b200.KombGpuError):
+        ctx.analyse_hits(rk, ut, n, edge_capacity=exp_edges.shape[0] - 1)
+    g, r = ctx.analyse_hits(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 0)       # empty input
+    with g:
+        assert r["u"].shape == (0,) and r["score"].shape == (0,)
+
+
 def test_densest_core(ctx, oracle_mod):
     """kombgpu_graph_densest_core against the numpy checker, plus known answers: a K_40 planted in a sparse graph is
     the densest core (density 19.5 = C(40,2)/40); an empty graph gives level 0."""
