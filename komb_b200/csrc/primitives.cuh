@@ -7,15 +7,37 @@
 
 namespace kg {
 
-// One radix pass sorts on bits [shift, shift+bits) (bits <= 8).
+// One radix pass sorts on a digit of at most 8 bits: key bits [shift, shift+bits), and above them (when bits2 > 0)
+// key bits [shift2, shift2+bits2) -- a digit may straddle the gap between two key fields, so that e.g. a
+// (20 + 20)-bit pair key takes 5 passes of 8 bits instead of 3 + 3 passes of 7.
 struct RadixPass {
     int shift;
     int bits;
+    int shift2;
+    int bits2;
 };
 
-// Split the key bit ranges [lo0,hi0) and [lo1,hi1) (second may be empty) into
-// passes of at most 8 bits, least significant first.
+// Split the key bit ranges [lo0,hi0) and [lo1,hi1) (second may be empty), read as one bit string, into the
+// fewest passes of at most 8 bits (equal widths), least significant first.
 int plan_radix_passes(int lo0, int hi0, int lo1, int hi1, RadixPass *out /* >= 8 entries */);
+
+#ifdef __CUDACC__
+// digit extraction shared by every sort kernel
+struct DigitSpec {
+    int shift, shift2, bits1;
+    uint32_t mask1, mask2, mask;   // mask = all digit bits
+    __host__ __device__ static DigitSpec of(const RadixPass &p) {
+        DigitSpec d;
+        d.shift = p.shift; d.shift2 = p.shift2; d.bits1 = p.bits;
+        d.mask1 = (1u << p.bits) - 1u; d.mask2 = (1u << p.bits2) - 1u;
+        d.mask = (1u << (p.bits + p.bits2)) - 1u;
+        return d;
+    }
+    __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
+        return ((uint32_t)(key >> shift) & mask1) | (((uint32_t)(key >> shift2) & mask2) << bits1);
+    }
+};
+#endif
 
 // Stable LSD radix sort.  `a` holds the keys, `b` is scratch of the same size;
 // returns in *sorted whichever of the two holds the result.

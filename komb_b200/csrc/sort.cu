@@ -26,9 +26,9 @@ constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRadix = 256;
 
 // table[d * n_tiles + tile] = number of keys of this tile whose digit is d
-__global__ void __launch_bounds__(kRsThreads) radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift,
-                                                                uint32_t mask, uint32_t *__restrict__ table,
-                                                                uint32_t n_tiles) {
+__global__ void __launch_bounds__(kRsThreads) radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, DigitSpec dg,
+                                                                uint32_t *__restrict__ table, uint32_t n_tiles) {
+    const uint32_t mask = dg.mask;
     __shared__ uint32_t s_hist[kRadix];
     for (int d = threadIdx.x; d < kRadix; d += kRsThreads) s_hist[d] = 0;
     __syncthreads();
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kRsThreads) radix_hist_kernel(const uint64_t *
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         uint64_t i = base + (uint64_t)j * kRsThreads + threadIdx.x;
-        if (i < n) atomicAdd(&s_hist[(uint32_t)(keys[i] >> shift) & mask], 1u);
+        if (i < n) atomicAdd(&s_hist[dg(keys[i])], 1u);
     }
     __syncthreads();
     for (int d = threadIdx.x; d <= (int)mask; d += kRsThreads) table[(uint64_t)d * n_tiles + blockIdx.x] = s_hist[d];
@@ -61,10 +61,11 @@ struct ScatterSmem {
 };
 
 __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
-                                                                   uint64_t n, int shift, uint32_t mask,
+                                                                   uint64_t n, DigitSpec dg,
                                                                    const uint32_t *__restrict__ table, uint32_t n_tiles) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(s_raw);
+    const uint32_t mask = dg.mask;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint64_t tile_base = (uint64_t)blockIdx.x * kRsTile;
     const uint32_t tile_count = (uint32_t)min((uint64_t)kRsTile, n - tile_base);
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(const uint64_
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         const bool valid = e < tile_count;
-        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : 0u;
+        const uint32_t d = valid ? dg(key[j]) : 0u;
         uint32_t same = __ballot_sync(kFullMask, valid);
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(const uint64_
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         if (e < tile_count) {
-            const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+            const uint32_t d = dg(key[j]);
             s.keys[s.digit_local[d] + s.warp_cnt[warp][d] + rank[j]] = key[j];
         }
     }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(const uint64_
     // contiguous runs out to global memory
     for (uint32_t i = threadIdx.x; i < tile_count; i += kRsThreads) {
         const uint64_t k = s.keys[i];
-        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        const uint32_t d = dg(k);
         out[(uint64_t)(s.digit_global[d] + i)] = k;
     }
 }
@@ -173,8 +174,7 @@ constexpr uint32_t kFlagAgg = 1u << 30, kFlagPrefix = 2u << 30, kValueMask = (1u
 constexpr int kMaxPasses = 8;
 
 struct PassList {
-    int shift[kMaxPasses];
-    uint32_t mask[kMaxPasses];
+    DigitSpec dg[kMaxPasses];
     int n;
 };
 
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kRsThreads) radix_global_hist_kernel(const uin
             const bool valid = i < n;
             const bool full = __all_sync(kFullMask, valid);
             for (int p = 0; p < pl.n; ++p) {
-                const uint32_t d = (uint32_t)(key[j] >> pl.shift[p]) & pl.mask[p];
+                const uint32_t d = pl.dg[p](key[j]);
                 // sorted or narrow digits put a whole warp on one counter: count it once
                 const uint32_t d0 = __shfl_sync(kFullMask, d, 0);
                 if (full && __all_sync(kFullMask, d == d0)) {
@@ -247,13 +247,13 @@ struct SweepSmem {
 // slow ADU pipe; ranking a few of the 8 items with it spreads the work over both pipes.
 template <int kBits, int kMatch>
 __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
-                                                                    uint64_t n, int shift, uint32_t mask,
+                                                                    uint64_t n, DigitSpec dg,
                                                                     const uint32_t *__restrict__ digit_base,  // exclusive global histogram of this pass
                                                                     uint32_t *status, uint32_t *tile_counter) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SweepSmem &s = *reinterpret_cast<SweepSmem *>(s_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    if (kBits) mask = (1u << kBits) - 1u;
+    const uint32_t mask = kBits ? (1u << kBits) - 1u : dg.mask;
     if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
     for (int i = threadIdx.x; i < kSwWarps * kRadix; i += kSwThreads) (&s.warp_cnt[0][0])[i] = 0;
     __syncthreads();
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(c
     for (int j = 0; j < kSwItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         const bool valid = e < tile_count;
-        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : 0u;
+        const uint32_t d = valid ? dg(key[j]) : 0u;
         uint32_t same;
         if (j < kMatch) {
             same = __match_any_sync(kFullMask, valid ? d : 0xffffffffu);   // invalid lanes (tail of the last tile) group apart
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(c
     for (int j = 0; j < kSwItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         if (e < tile_count) {
-            const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+            const uint32_t d = dg(key[j]);
             s.keys[s.digit_local[d] + s.warp_cnt[warp][d] + rank[j]] = key[j];
         }
     }
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(c
     // contiguous runs out to global memory
     for (uint32_t i = threadIdx.x; i < tile_count; i += kSwThreads) {
         const uint64_t k = s.keys[i];
-        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        const uint32_t d = dg(k);
         out[(uint64_t)(s.digit_global[d] + i)] = k;
     }
 }
@@ -370,19 +370,19 @@ __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(c
 }  // namespace
 
 int plan_radix_passes(int lo0, int hi0, int lo1, int hi1, RadixPass *out) {
+    const int len0 = hi0 > lo0 ? hi0 - lo0 : 0, len1 = hi1 > lo1 ? hi1 - lo1 : 0;
+    const int total = len0 + len1;
+    if (total <= 0) return 0;
+    const int np = (total + 7) / 8;
+    const int w = (total + np - 1) / np;
     int n = 0;
-    const int lo[2] = {lo0, lo1}, hi[2] = {hi0, hi1};
-    for (int r = 0; r < 2; ++r) {
-        int bits = hi[r] - lo[r];
-        if (bits <= 0) continue;
-        int np = (bits + 7) / 8;
-        int w = (bits + np - 1) / np;
-        int s = lo[r];
-        while (s < hi[r]) {
-            int b = hi[r] - s < w ? hi[r] - s : w;
-            out[n++] = RadixPass{s, b};
-            s += b;
-        }
+    for (int v = 0; v < total; v += w) {            // virtual bits [v, e) of the concatenated ranges
+        const int e = v + w < total ? v + w : total;
+        RadixPass p{0, 0, 0, 0};
+        if (e <= len0) { p.shift = lo0 + v; p.bits = e - v; }                       // inside the first range
+        else if (v >= len0) { p.shift = lo1 + (v - len0); p.bits = e - v; }          // inside the second range
+        else { p.shift = lo0 + v; p.bits = len0 - v; p.shift2 = lo1; p.bits2 = e - len0; }   // straddles the gap
+        out[n++] = p;
     }
     return n;
 }
@@ -417,20 +417,21 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
         KG_CUDA(ctx, cudaMemsetAsync(ws.p, 0, (head + (size_t)n_passes * n_tiles * kRadix) * sizeof(uint32_t), ctx->stream));
         PassList pl{};
         pl.n = n_passes;
-        for (int p = 0; p < n_passes; ++p) { pl.shift[p] = passes[p].shift; pl.mask[p] = (1u << passes[p].bits) - 1u; }
+        for (int p = 0; p < n_passes; ++p) pl.dg[p] = DigitSpec::of(passes[p]);
         const uint32_t hist_grid = min(n_tiles, (uint32_t)ctx->sm_count * 4u);
         KG_LAUNCH(ctx, radix_global_hist_kernel, hist_grid, kRsThreads, 0, src, n, pl, ws.p);
         KG_LAUNCH(ctx, radix_hist_scan_kernel, n_passes, kRadix, 0, ws.p);
         for (int p = 0; p < n_passes; ++p) {
             const uint32_t *dbase = ws.p + (size_t)p * kRadix;
+            const bool w8 = passes[p].bits + passes[p].bits2 == 8;
             uint32_t *status = ws.p + head + (size_t)p * n_tiles * kRadix, *counter = ws.p + (size_t)n_passes * kRadix + p;
 #define KG_SWEEP(BITS, MATCH)                                                                                        \
-    KG_LAUNCH(ctx, (radix_sweep_kernel<BITS, MATCH>), n_tiles, kSwThreads, sizeof(SweepSmem), src, dst, n, pl.shift[p], \
-              pl.mask[p], dbase, status, counter)
-            if (n_match == 8) { if (passes[p].bits == 8) KG_SWEEP(8, 8); else KG_SWEEP(0, 8); }
-            else if (n_match == 4) { if (passes[p].bits == 8) KG_SWEEP(8, 4); else KG_SWEEP(0, 4); }
-            else if (n_match == 2) { if (passes[p].bits == 8) KG_SWEEP(8, 2); else KG_SWEEP(0, 2); }
-            else { if (passes[p].bits == 8) KG_SWEEP(8, 0); else KG_SWEEP(0, 0); }
+    KG_LAUNCH(ctx, (radix_sweep_kernel<BITS, MATCH>), n_tiles, kSwThreads, sizeof(SweepSmem), src, dst, n, pl.dg[p], \
+              dbase, status, counter)
+            if (n_match == 8) { if (w8) KG_SWEEP(8, 8); else KG_SWEEP(0, 8); }
+            else if (n_match == 4) { if (w8) KG_SWEEP(8, 4); else KG_SWEEP(0, 4); }
+            else if (n_match == 2) { if (w8) KG_SWEEP(8, 2); else KG_SWEEP(0, 2); }
+            else { if (w8) KG_SWEEP(8, 0); else KG_SWEEP(0, 0); }
 #undef KG_SWEEP
             uint64_t *t = src; src = dst; dst = t;
         }
@@ -440,12 +441,11 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
     DevBuf<uint32_t> table;
     KG_ALLOC(ctx, table, (size_t)kRadix * n_tiles);
     for (int p = 0; p < n_passes; ++p) {
-        const int shift = passes[p].shift;
-        const uint32_t mask = (1u << passes[p].bits) - 1u;
-        const uint64_t table_len = (uint64_t)(mask + 1) * n_tiles;
-        KG_LAUNCH(ctx, radix_hist_kernel, n_tiles, kRsThreads, 0, src, n, shift, mask, table.p, n_tiles);
+        const DigitSpec dg = DigitSpec::of(passes[p]);
+        const uint64_t table_len = (uint64_t)(dg.mask + 1) * n_tiles;
+        KG_LAUNCH(ctx, radix_hist_kernel, n_tiles, kRsThreads, 0, src, n, dg, table.p, n_tiles);
         KG_TRY((device_scan<uint32_t>(ctx, table_len, TableIn{table.p}, TableOut{table.p}, (uint32_t *)nullptr)));
-        KG_LAUNCH(ctx, radix_scatter_kernel, n_tiles, kRsThreads, sizeof(ScatterSmem), src, dst, n, shift, mask, table.p, n_tiles);
+        KG_LAUNCH(ctx, radix_scatter_kernel, n_tiles, kRsThreads, sizeof(ScatterSmem), src, dst, n, dg, table.p, n_tiles);
         uint64_t *t = src; src = dst; dst = t;
     }
     *sorted = src;

@@ -16,7 +16,7 @@ for mode in (sys.argv[1:] or ["legacy", "sweep"]):
     for name, n, lo, hi, srt in SHAPES:
         ms, ok = ctypes.c_float(), ctypes.c_int()
         rc = lib.kombgpu_debug_sort_u64(ctx._h, n, lo, hi, srt, 3, ctypes.byref(ms), ctypes.byref(ok))
-        passes = (lo + 7) // 8 + (hi + 7) // 8
+        passes = (lo + hi + 7) // 8
         gbs = passes * 16 * n / ms.value / 1e6 if rc == 0 else 0
         print(json.dumps({"mode": mode, "shape": name, "rc": rc, "ok": ok.value, "ms": round(ms.value, 3), "passes": passes,
                           "GBs_rw_per_pass": round(gbs, 1)}), flush=True)
