@@ -418,6 +418,8 @@ def run_ours_multi(args, rank, world, local_rank):
     stage_t.clear()
     stage_t.update(saved)
 
+    # every rank's view of the stage times (rank 0's alone hides the skew the first collective absorbs)
+    per_rank = comm.all_gather_ints([int(1e3 * 1e3 * saved.get(k, 0.0) / max(args.steps, 1)) for k in ("build", "gather.counts", "gather.deg", "gather.col", "gather", "peel+corea")])
     tot = comm.all_gather_ints([rk_h.numel(), d2h])
     H = int(tot[:, 0].sum())
     E, n = res.n_edges, n_global
@@ -425,7 +427,7 @@ def run_ours_multi(args, rank, world, local_rank):
     b_peel = 24 * E + 16 * n
     steps = max(args.steps, 1)
     build_s = stage_t.get("build", 0.0) / steps
-    gather_s = stage_t.get("gather", 0.0) / steps
+    gather_s = sum(v for k, v in stage_t.items() if k.startswith("gather")) / steps   # counts + degree + col + release
     if res.stats["peel_mode"] == "gather":
         peel_s = res.stats["ms_peel"] * 1e-3
         corea_s = res.stats["ms_corea"] * 1e-3
@@ -449,6 +451,8 @@ def run_ours_multi(args, rank, world, local_rank):
                        "l2": "256 MB flush between timed steps; inputs exceed L2"},
             "stages": {"build": {"ms": build_s * 1e3, "hits_per_s": H / build_s if build_s else None},
                        "gather_csr": {"ms": gather_s * 1e3},
+                       "per_rank_ms": {name: [x / 1e3 for x in per_rank[:, i].tolist()] for i, name in
+                                       enumerate(("build", "gather.counts", "gather.deg", "gather.col", "gather.release", "peel+corea"))},
                        "peel": {"ms": peel_s * 1e3, "edges_per_s": E / peel_s if peel_s else None, "algorithmic_bytes": b_peel,
                                 "frac_hbm": (b_peel / peel_s / 1e9 / (hbm_gbs * world)) if peel_s else None},
                        "corea": {"ms": corea_s * 1e3, "vertices_per_s": n / corea_s if corea_s else None},

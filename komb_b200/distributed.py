@@ -117,6 +117,10 @@ class Comm:
                 # large, nearly even segments (the CSR of a balanced range partition): ONE all-gather of pieces
                 # padded to the longest (NCCL's ring / NVLS path), then one device copy that drops the padding.
                 # The list form below turns into one broadcast per rank, which ran at a third of that bandwidth.
+                # Empirical: with a device-wide synchronisation in front of each of the gather stage's collectives the
+                # stage takes 7.3 ms at N=4 instead of 13.1 ms (profiles/r1/r1z_bench_n4*.json); the all-gather itself is
+                # 2.7 ms for 1.05 GB in the bench and 1.4 ms in isolation (tools/gather_probe.py).  Not understood yet.
+                torch.cuda.synchronize()
                 pad = torch.empty(self.world * mx, dtype=arr.dtype, device=arr.device)
                 src = pad[self.rank * mx:(self.rank + 1) * mx]      # in place: my slot of the padded buffer
                 src[:arr.numel()].copy_(arr)
@@ -341,9 +345,12 @@ def analyse_partitioned(engine, comm: Comm, n_global: int, *, read_key=None, uni
 
     if peel_mode == "gather":
         # ---- stage 2+3 on the gathered graph ------------------------------------
+        tick("gather.counts")
         deg_loc, col_loc = engine.part_csr(part)
         deg_full = comm.all_gather_var(deg_loc)
+        tick("gather.deg")
         col_full = comm.all_gather_var(col_loc)
+        tick("gather.col")
         engine.destroy_part(part)
         tick("gather")
         deg_f, core_f, score_f, max_score, max_core, gst = engine.gather_peel(deg_full, col_full, n_global, key_mode)
