@@ -230,6 +230,22 @@ def test_analyse_hits_one_call(ctx, oracle_mod):
         assert r["u"].shape == (0,) and r["score"].shape == (0,)
 
 
+@pytest.mark.parametrize("mode", ["sweep", "legacy"])
+def test_radix_sort_shapes(ctx, monkeypatch, mode):
+    """kombgpu_debug_sort_u64: both pass implementations give a sorted permutation on the key shapes the path sorts
+    (two key fields with a gap, digits that straddle it, narrow last digits, non-decreasing high field, one field
+    only, a partial last tile, fewer keys than a tile)."""
+    import ctypes
+    from komb_b200 import _lib
+    monkeypatch.setenv("KOMBGPU_SORT", mode)
+    lib = _lib.load()
+    for n, lo, hi, srt in [(1_000_003, 20, 20, 0), (777_777, 20, 23, 1), (500_000, 0, 20, 0), (300_000, 26, 26, 0), (4097, 13, 3, 0),
+                           (100, 5, 0, 0), (1, 8, 8, 0), (2_000_000, 32, 32, 0)]:
+        ms, ok = ctypes.c_float(), ctypes.c_int()
+        rc = lib.kombgpu_debug_sort_u64(ctx._h, n, lo, hi, srt, 1, ctypes.byref(ms), ctypes.byref(ok))
+        assert rc == 0 and ok.value == 1, (n, lo, hi, srt, rc, ok.value)
+
+
 def test_densest_core(ctx, oracle_mod):
     """kombgpu_graph_densest_core against the numpy checker, plus known answers: a K_40 planted in a sparse graph is
     the densest core (density 19.5 = C(40,2)/40); an empty graph gives level 0."""
