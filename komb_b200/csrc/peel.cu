@@ -177,7 +177,7 @@ int peel_coreness(kombgpu_graph *g) {
     // every vertex enters the pool at most once; a row is sliced at most once (<= 2E/kSplit long rows, each giving
     // <= len/kSliceLen + 1 slices); plus the slots idle CTAs reserve past the tail
     // (warp mode re-queues the pieces of rows longer than kWarpSplit, through the pool when the CTA's ring is busy)
-    const uint64_t cap64 = (uint64_t)n + 2 * g->n_edges / kSliceLen + 2 * g->n_edges / kSplit + 4 * g->n_edges / kWarpSplitMin +
+    const uint64_t cap64 = (uint64_t)n + 2 * g->n_edges / kWarpSplitMin + 2 * g->n_edges / kSplit + 4 * g->n_edges / kWarpSplitMin +
                            (uint64_t)grid * kClaimMax + 64;
     if (cap64 >= 0xffffffffull || 2 * g->n_edges >= (1ull << (62 - kSliceLenBits)))
         return ctx_fail(ctx, KOMBGPU_EINVAL, "graph too large for the pool encoding");
@@ -193,10 +193,12 @@ int peel_coreness(kombgpu_graph *g) {
     init.tune[1] = kWarpSplit;
     init.tune[2] = 0;
     init.tune[3] = kThinEdges;
+    init.tune[4] = kSliceLen;
     if (const char *e = getenv("KOMBGPU_PEEL_KEEP")) init.tune[0] = (uint32_t)atoi(e);
     if (const char *e = getenv("KOMBGPU_PEEL_WSPLIT")) init.tune[1] = (uint32_t)atoi(e) < kWarpSplitMin ? kWarpSplitMin : (uint32_t)atoi(e);
     if (const char *e = getenv("KOMBGPU_PEEL_PARK")) init.tune[2] = (uint32_t)atoi(e);
     if (const char *e = getenv("KOMBGPU_PEEL_THIN")) init.tune[3] = (uint32_t)atoi(e);
+    if (const char *e = getenv("KOMBGPU_PEEL_HUBSLICE")) init.tune[4] = (uint32_t)atoi(e) < kWarpSplitMin ? kWarpSplitMin : (uint32_t)atoi(e);
     DevBuf<unsigned long long> trace;
     const char *trace_path = getenv("KOMBGPU_TRACE");
     const uint32_t trace_cap = 1u << 16;

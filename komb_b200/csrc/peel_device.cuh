@@ -64,7 +64,7 @@ struct PeelState {
     unsigned long long batches;    // traversals over all CTAs
     unsigned long long *trace;     // optional (KOMBGPU_TRACE): 6 words per round, CTA 0's view
     uint32_t trace_cap;
-    uint32_t tune[4];              // warp mode knobs (peel_warp.cuh WarpTune): keep, wsplit, park_ns, thin
+    uint32_t tune[8];              // warp mode knobs (peel_warp.cuh WarpTune): keep, wsplit, park_ns, thin, hub_slice
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {

@@ -46,6 +46,7 @@ struct WarpTune {
     uint32_t wsplit;   // edges of a row one warp keeps
     uint32_t park_ns;  // sleep between two polls of a parked warp (0 = spin)
     uint32_t thin;     // a batch up to this many edges may hand its discoveries on in registers
+    uint32_t hub_slice;  // edges per pool slice of a row longer than kSplit
 };
 
 struct WarpShared {
@@ -109,11 +110,11 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const uint32_
             my_len = (uint32_t)(row_ptr[v + 1] - my_row);
             if (my_len > kSplit) {
                 // hub row: hand it to the whole grid as slices
-                const uint32_t n_sl = (my_len + kSliceLen - 1) / kSliceLen;
+                const uint32_t n_sl = (my_len + tn.hub_slice - 1) / tn.hub_slice;
                 const uint32_t s0 = atomicAdd(&st->q_tail, n_sl);
                 for (uint32_t i = 0; i < n_sl; ++i) {
-                    const uint64_t e = kSliceBit | ((my_row + (uint64_t)i * kSliceLen) << kSliceLenBits) |
-                                       min(kSliceLen, my_len - i * kSliceLen);
+                    const uint64_t e = kSliceBit | ((my_row + (uint64_t)i * tn.hub_slice) << kSliceLenBits) |
+                                       min(tn.hub_slice, my_len - i * tn.hub_slice);
                     if (s0 + i < cap) st_volatile_u64(&Q[s0 + i], e);
                     else atomicExch(&st->error, 3u);
                 }
@@ -444,6 +445,7 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
     tn.wsplit = st->tune[1];
     tn.park_ns = st->tune[2];
     tn.thin = st->tune[3];
+    tn.hub_slice = st->tune[4];
     uint32_t rb = 0, re = 0;   // ring tickets this warp owns
     uint32_t removed = 0, n_shared = 0, batches = 0;
     uint32_t spins = 0;
