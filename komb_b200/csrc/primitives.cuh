@@ -3,6 +3,8 @@
 // compaction) and an LSD radix sort of 64-bit keys.  All HBM-bound integer work.
 #pragma once
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kg {
@@ -104,6 +106,78 @@ __global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint64_t n
     }
 }
 
+// Single-pass scan (chained scan with decoupled look-back; opt-in, see device_scan): every element's in(i) is evaluated ONCE (some of the
+// path's functors look back through a read or compare neighbouring keys), a thread owns 16 consecutive elements
+// (one CTA-wide scan per tile instead of sixteen), tiles take their index from a counter and learn the sum of all
+// earlier tiles from 64-bit status words (2 flag bits + 62-bit value: every sum on this path is far below 2^62),
+// 32 predecessors per look-back step.
+constexpr uint64_t kScanFlagAgg = 1ull << 62, kScanFlagPrefix = 2ull << 62, kScanValueMask = (1ull << 62) - 1;
+
+template <typename T, typename InFn, typename OutFn>
+__global__ void __launch_bounds__(kScanThreads) scan_onepass_kernel(uint64_t n, InFn in, OutFn out, uint64_t *status,
+                                                                    uint32_t *tile_counter, uint32_t n_tiles, T *total) {
+    __shared__ T s_scan[kScanThreads / 32 + 1];
+    __shared__ uint64_t s_excl;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t first = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    T v[kScanItems];
+    T sum = T(0);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        v[j] = first + j < n ? in(first + j) : T(0);
+        sum += v[j];
+    }
+    T tile_total;
+    const T ex = block_excl_scan_add<T, kScanThreads>(sum, s_scan, &tile_total);
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        uint64_t excl = 0;
+        if (lane == 0)
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile),
+                         "l"((tile == 0 ? kScanFlagPrefix : kScanFlagAgg) | (uint64_t)tile_total) : "memory");
+        if (tile > 0) {
+            int64_t p = (int64_t)tile - 1;   // lane l looks at tile p - l
+            while (true) {
+                const int64_t idx = p - (int64_t)lane;
+                uint64_t w = kScanFlagPrefix;   // before tile 0: an empty prefix
+                if (idx >= 0) {
+                    uint32_t spins = 0;
+                    do {
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(status + idx) : "memory");
+                        if (++spins > (1u << 28)) __trap();
+                    } while ((w >> 62) == 0);
+                }
+                const uint32_t pm = __ballot_sync(kFullMask, (w & kScanFlagPrefix) != 0);
+                // tiles p .. p - f contribute (f = nearest predecessor that already knows its inclusive prefix)
+                const uint32_t f = pm ? (uint32_t)__ffs(pm) - 1u : 31u;
+                uint64_t part = lane <= f ? (w & kScanValueMask) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+                excl += part;
+                if (pm) break;
+                p -= 32;
+            }
+            if (lane == 0)
+                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(kScanFlagPrefix | (excl + (uint64_t)tile_total))
+                             : "memory");
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (tile == n_tiles - 1 && total) *total = (T)(excl + (uint64_t)tile_total);
+        }
+    }
+    __syncthreads();
+    T carry = (T)s_excl + ex;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (first + j < n) out(first + j, carry, v[j]);
+        carry += v[j];
+    }
+}
+
 // Exclusive prefix sum over in(0..n-1); out(i, prefix, value) is called once per
 // element; *total_dev (device, optional) receives the grand total.
 template <typename T, typename InFn, typename OutFn>
@@ -113,6 +187,19 @@ int device_scan(kombgpu_ctx *ctx, uint64_t n, InFn in, OutFn out, T *total_dev) 
         return KOMBGPU_OK;
     }
     uint32_t n_tiles = ceil_div_u64(n, kScanTile);
+    // Measured on the cfg2 step (bench.py): the single-pass scan makes the build 0.7 ms SLOWER (4.58 against 3.87 ms).
+    // Its blocked layout (16 consecutive elements per thread) turns the functors' key reads and the compaction's
+    // writes into 128-byte-strided accesses, which costs more than the second evaluation of in(i) it saves.  It stays
+    // selectable (KOMBGPU_SCAN=onepass); the default is the three-kernel scan with coalesced, striped accesses.
+    static const bool onepass = getenv("KOMBGPU_SCAN") != nullptr && getenv("KOMBGPU_SCAN")[0] == 'o';
+    if (onepass) {
+        DevBuf<uint64_t> status;   // [n_tiles status words | tile counter]
+        KG_ALLOC(ctx, status, (size_t)n_tiles + 1);
+        KG_CUDA(ctx, cudaMemsetAsync(status.p, 0, ((size_t)n_tiles + 1) * sizeof(uint64_t), ctx->stream));
+        KG_LAUNCH(ctx, (scan_onepass_kernel<T, InFn, OutFn>), n_tiles, kScanThreads, 0, n, in, out, status.p,
+                  reinterpret_cast<uint32_t *>(status.p + n_tiles), n_tiles, total_dev);
+        return KOMBGPU_OK;
+    }
     DevBuf<T> tiles;
     KG_ALLOC(ctx, tiles, n_tiles);
     KG_LAUNCH(ctx, (scan_reduce_kernel<T, InFn>), n_tiles, kScanThreads, 0, n, in, tiles.p);
