@@ -106,34 +106,48 @@ __global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint64_t n
     }
 }
 
-// Single-pass scan (chained scan with decoupled look-back; opt-in, see device_scan): every element's in(i) is evaluated ONCE (some of the
-// path's functors look back through a read or compare neighbouring keys), a thread owns 16 consecutive elements
-// (one CTA-wide scan per tile instead of sixteen), tiles take their index from a counter and learn the sum of all
-// earlier tiles from 64-bit status words (2 flag bits + 62-bit value: every sum on this path is far below 2^62),
-// 32 predecessors per look-back step.
+// Single-pass scan (chained scan with decoupled look-back): every element's in(i) is evaluated ONCE (some of the
+// path's functors look back through a read or compare neighbouring keys) and every access stays coalesced (item j of
+// thread t is element base + j * threads + t).  Inside a tile: one warp scan per item, the 16 x 16 (item, warp)
+// totals scanned once by the CTA -- two barriers instead of the three per item of the downsweep kernel.  Tiles
+// take their index from a counter and learn the sum of all earlier tiles from 64-bit status words (2 flag bits +
+// 62-bit value: every sum on this path is far below 2^62), 32 predecessors per look-back step.
 constexpr uint64_t kScanFlagAgg = 1ull << 62, kScanFlagPrefix = 2ull << 62, kScanValueMask = (1ull << 62) - 1;
+template <typename T> struct ScanShape { static constexpr int kItems = sizeof(T) > 4 ? 8 : 16; };   // registers: v[] + wex[]
 
 template <typename T, typename InFn, typename OutFn>
 __global__ void __launch_bounds__(kScanThreads) scan_onepass_kernel(uint64_t n, InFn in, OutFn out, uint64_t *status,
                                                                     uint32_t *tile_counter, uint32_t n_tiles, T *total) {
-    __shared__ T s_scan[kScanThreads / 32 + 1];
+    constexpr int kItems = ScanShape<T>::kItems;
+    constexpr int kWarps = kScanThreads / 32;
+    __shared__ T s_tot[kItems * kWarps];
+    __shared__ T s_scan[kWarps + 1];
     __shared__ uint64_t s_excl;
     __shared__ uint32_t s_tile;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t first = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    T v[kScanItems];
-    T sum = T(0);
+    const uint64_t base = (uint64_t)tile * (kScanThreads * kItems);
+    T v[kItems], wex[kItems];
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        v[j] = first + j < n ? in(first + j) : T(0);
-        sum += v[j];
+    for (int j = 0; j < kItems; ++j) {
+        const uint64_t i = base + (uint64_t)j * kScanThreads + threadIdx.x;
+        v[j] = i < n ? in(i) : T(0);
     }
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const T incl = warp_incl_scan_add(v[j]);
+        wex[j] = incl - v[j];
+        if (lane == 31) s_tot[j * kWarps + warp] = incl;
+    }
+    __syncthreads();
+    // (item, warp) totals in element order: item-major
+    const T mine = threadIdx.x < kItems * kWarps ? s_tot[threadIdx.x] : T(0);
     T tile_total;
-    const T ex = block_excl_scan_add<T, kScanThreads>(sum, s_scan, &tile_total);
+    const T off = block_excl_scan_add<T, kScanThreads>(mine, s_scan, &tile_total);
+    if (threadIdx.x < kItems * kWarps) s_tot[threadIdx.x] = off;
     if (threadIdx.x < 32) {
-        const uint32_t lane = threadIdx.x;
         uint64_t excl = 0;
         if (lane == 0)
             asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile),
@@ -170,11 +184,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_onepass_kernel(uint64_t n, 
         }
     }
     __syncthreads();
-    T carry = (T)s_excl + ex;
+    const T tile_base = (T)s_excl;
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        if (first + j < n) out(first + j, carry, v[j]);
-        carry += v[j];
+    for (int j = 0; j < kItems; ++j) {
+        const uint64_t i = base + (uint64_t)j * kScanThreads + threadIdx.x;
+        if (i < n) out(i, tile_base + s_tot[j * kWarps + warp] + wex[j], v[j]);
     }
 }
 
@@ -186,13 +200,10 @@ int device_scan(kombgpu_ctx *ctx, uint64_t n, InFn in, OutFn out, T *total_dev) 
         if (total_dev) KG_CUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(T), ctx->stream));
         return KOMBGPU_OK;
     }
-    uint32_t n_tiles = ceil_div_u64(n, kScanTile);
-    // Measured on the cfg2 step (bench.py): the single-pass scan makes the build 0.7 ms SLOWER (4.58 against 3.87 ms).
-    // Its blocked layout (16 consecutive elements per thread) turns the functors' key reads and the compaction's
-    // writes into 128-byte-strided accesses, which costs more than the second evaluation of in(i) it saves.  It stays
-    // selectable (KOMBGPU_SCAN=onepass); the default is the three-kernel scan with coalesced, striped accesses.
-    static const bool onepass = getenv("KOMBGPU_SCAN") != nullptr && getenv("KOMBGPU_SCAN")[0] == 'o';
-    if (onepass) {
+    // KOMBGPU_SCAN=legacy: the three-kernel scan (reduce, tile prefixes, downsweep), kept for A/B runs
+    static const bool legacy = getenv("KOMBGPU_SCAN") != nullptr && getenv("KOMBGPU_SCAN")[0] == 'l';
+    if (!legacy) {
+        const uint32_t n_tiles = ceil_div_u64(n, (uint64_t)kScanThreads * ScanShape<T>::kItems);
         DevBuf<uint64_t> status;   // [n_tiles status words | tile counter]
         KG_ALLOC(ctx, status, (size_t)n_tiles + 1);
         KG_CUDA(ctx, cudaMemsetAsync(status.p, 0, ((size_t)n_tiles + 1) * sizeof(uint64_t), ctx->stream));
@@ -200,6 +211,7 @@ int device_scan(kombgpu_ctx *ctx, uint64_t n, InFn in, OutFn out, T *total_dev) 
                   reinterpret_cast<uint32_t *>(status.p + n_tiles), n_tiles, total_dev);
         return KOMBGPU_OK;
     }
+    uint32_t n_tiles = ceil_div_u64(n, kScanTile);
     DevBuf<T> tiles;
     KG_ALLOC(ctx, tiles, n_tiles);
     KG_LAUNCH(ctx, (scan_reduce_kernel<T, InFn>), n_tiles, kScanThreads, 0, n, in, tiles.p);
