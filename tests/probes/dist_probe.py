@@ -1,8 +1,8 @@
 """Scale probe of the partitioned path: world 2 as two processes over gloo on whatever GPUs exist.
-usage: python tools/dist_probe.py n_unitigs n_read_pairs [world]"""
+usage: python tests/probes/dist_probe.py n_unitigs n_read_pairs [world]"""
 import os, pickle, socket, sys, tempfile, time
 from pathlib import Path
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np
 import torch.multiprocessing as mp

@@ -1,8 +1,8 @@
 """Wall time of the komb2 drop-in against the reference binary on the same SAM pair (cfg2 read sample):
-   dropin_probe.py [read_pairs=625000] [threads]"""
+   tests/probes/dropin_probe.py [read_pairs=625000] [threads]"""
 import os, re, subprocess, sys, tempfile, time
 from pathlib import Path
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from komb_b200 import synth
 from oracle import oracle

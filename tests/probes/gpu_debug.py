@@ -1,11 +1,11 @@
 """Stage-by-stage bring-up check on a GPU box; logs progressively so that a hang
-is localised.  usage: python tools/gpu_debug.py [stage...]"""
+is localised.  usage: python tests/probes/gpu_debug.py [stage...]"""
 import os
 import sys
 import time
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 os.makedirs(ROOT / "gpurun_out", exist_ok=True)
 LOG = open(ROOT / "gpurun_out" / "debug.log", "a", buffering=1)

@@ -7,7 +7,7 @@ Inputs are generated on the device (torch); the path runs through the C ABI's de
 points.  Checks: (1) k-core certificate on the GPU: every vertex has >= core(v) neighbours of coreness
 >= core(v) (so the assignment is feasible: core <= true coreness) and <= core(v) neighbours of
 coreness > core(v) (necessary for maximality); (2) --oracle: bit-exact comparison with the CPU BZ
-oracle on the same edges; (3) CORE-A against the oracle's on the GPU's (coreness, degree)."""
+oracle on the same edges and CORE-A against the oracle's (the checker itself is tests/probes/scale_oracle_check.py)."""
 import argparse, json, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -110,20 +110,10 @@ def main():
     c1, c2, c3 = certificate(core, col, deg, n)
     print(f"certificate: feasible={c1} no-vertex-misses-a-higher-core={c2} core<=deg={c3} ({time.perf_counter() - t0:.1f} s)", flush=True)
     out.update({"cert_feasible": c1, "cert_maximal_necessary": c2, "cert_core_le_deg": c3})
-    if a.oracle:
-        from oracle import oracle
-        t0 = time.perf_counter()
-        eu, ev = g.edges()
-        edges = oracle.pack_edges(eu, ev)
-        odeg, ocore = oracle.coreness(n, edges)
-        t1 = time.perf_counter()
-        ok_d, ok_c = bool(np.array_equal(odeg, deg.cpu().numpy())), bool(np.array_equal(ocore, core.cpu().numpy()))
-        score = g.corea(komb_b200.KEY_EXACT64)
-        osc = oracle.corea(ocore, odeg, oracle.KEY_EXACT64)
-        ok_s = bool(np.allclose(score, osc, rtol=1e-6, atol=1e-12))
-        print(f"oracle (CPU BZ, {t1 - t0:.1f} s incl. D2H): degree equal {ok_d}, coreness equal {ok_c}, CORE-A within 1e-6 {ok_s}", flush=True)
-        out.update({"oracle_degree_equal": ok_d, "oracle_coreness_equal": ok_c, "oracle_corea_close": ok_s,
-                    "oracle_peel_edges_per_s": E / (t1 - t0)})
+    if a.oracle:   # the CPU checker lives with the tests: tests/probes/scale_oracle_check.py
+        sys.path.insert(0, str(ROOT / "tests" / "probes"))
+        from scale_oracle_check import check_against_oracle
+        out.update(check_against_oracle(g, n, deg, core))
     print(json.dumps(out), flush=True)
 
 
