@@ -115,3 +115,19 @@ def test_densest_core_checker_known_answers(oracle_mod):
     ring = oracle_mod.simplify(np.arange(8, dtype=np.uint32), ((np.arange(8) + 1) % 8).astype(np.uint32))
     _, core = oracle_mod.coreness(8, ring)
     assert oracle_mod.densest_core(core, ring) == {"k": 2, "n_vertices": 8, "n_edges": 8, "density": 1.0}
+
+
+def test_product_code_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under komb_b200/, host/, include/ or tools/ may import, link or
+    execute it (only tests/, __graft_entry__.smoke() and bench.py's CPU leg do)."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|oracle/_ref|libkomb_oracle|komb_oracle\.c", re.M)
+    offenders = []
+    for sub in ("komb_b200", "host", "include", "tools"):
+        for f in (root / sub).rglob("*"):
+            if f.is_file() and f.suffix in (".py", ".cu", ".cuh", ".h", ".hpp", ".cpp"):
+                if pat.search(f.read_text(errors="ignore")):
+                    offenders.append(str(f.relative_to(root)))
+    assert offenders == [], offenders
