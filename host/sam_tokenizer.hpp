@@ -46,7 +46,7 @@ class MappedFile {
         if (fstat(fd_, &st) != 0) return false;
         size = (size_t)st.st_size;
         if (size == 0) return true;
-        void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd_, 0);
+        void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd_, 0);   // pre-fault: parallel first-touch faults serialise on the mm lock
         if (m == MAP_FAILED) return false;
         madvise(m, size, MADV_SEQUENTIAL);
         data = static_cast<const char *>(m);
@@ -100,6 +100,9 @@ inline void tokenise_sam(const MappedFile &f, int threads, SamTokens &out, const
         SamTokens &loc = part[t];
         const char *p = base + cut[t];
         const char *stop = base + cut[t + 1];
+        // alignment records are rarely shorter than ~48 bytes: one allocation instead of a dozen doublings
+        loc.keys.reserve((size_t)(stop - p) / 48 + 16);
+        loc.rnames.reserve((size_t)(stop - p) / 48 + 16);
         while (p < stop) {
             const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(base + n - p)));
             if (!nl) break;  // unterminated final line: not processed (reference -t 1 behaviour)
@@ -136,15 +139,20 @@ inline void tokenise_sam(const MappedFile &f, int threads, SamTokens &out, const
     }
     for (int t = 0; t < threads; ++t)
         if (!err[t].empty()) throw std::runtime_error("malformed SAM " + path + ": " + err[t]);
-    size_t h = 0, s = 0;
-    for (auto &pt : part) { h += pt.keys.size(); s += pt.sq.size(); }
-    out.keys.reserve(out.keys.size() + h);
-    out.rnames.reserve(out.rnames.size() + h);
-    out.sq.reserve(out.sq.size() + s);
-    for (auto &pt : part) {
-        out.keys.insert(out.keys.end(), pt.keys.begin(), pt.keys.end());
-        out.rnames.insert(out.rnames.end(), pt.rnames.begin(), pt.rnames.end());
-        out.sq.insert(out.sq.end(), pt.sq.begin(), pt.sq.end());
+    // concatenate the per-thread parts in file order; every thread copies its own part to its final offset
+    std::vector<size_t> hit_off(threads + 1, out.keys.size()), sq_off(threads + 1, out.sq.size());
+    for (int t = 0; t < threads; ++t) {
+        hit_off[t + 1] = hit_off[t] + part[t].keys.size();
+        sq_off[t + 1] = sq_off[t] + part[t].sq.size();
+    }
+    out.keys.resize(hit_off[threads]);
+    out.rnames.resize(hit_off[threads]);
+    out.sq.resize(sq_off[threads]);
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; ++t) {
+        std::copy(part[t].keys.begin(), part[t].keys.end(), out.keys.begin() + hit_off[t]);
+        std::copy(part[t].rnames.begin(), part[t].rnames.end(), out.rnames.begin() + hit_off[t]);
+        std::copy(part[t].sq.begin(), part[t].sq.end(), out.sq.begin() + sq_off[t]);
     }
 }
 
@@ -254,14 +262,38 @@ inline InternResult intern_spans(const std::vector<Span> &items, int threads, bo
     std::vector<uint32_t> remap;  // provisional id (shard_base + local) -> final id
     res.first_index.resize(d);
     if (ordered) {
-        std::vector<std::pair<uint32_t, uint32_t>> by_first(d);  // (first item index, provisional id)
+        // final id = rank of the id's first item among all first items: flag the first items, prefix-sum the flags
+        // over the item array in parallel (no sort of the distinct ids)
+        std::vector<uint8_t> is_first(n, 0);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
         for (int s = 0; s < kShards; ++s)
-            for (size_t l = 0; l < shard_first[s].size(); ++l)
-                by_first[shard_base[s] + l] = {shard_first[s][l], shard_base[s] + (uint32_t)l};
-        std::sort(by_first.begin(), by_first.end());
+            for (uint32_t i : shard_first[s]) is_first[i] = 1;
+        std::vector<uint32_t> chunk_base(threads + 1, 0);
+        std::vector<uint32_t> rank_of_item(n);   // valid where is_first
+#pragma omp parallel num_threads(threads)
+        {
+            const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+            const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            uint32_t c = 0;
+            for (size_t i = lo; i < hi; ++i) c += is_first[i];
+            chunk_base[t + 1] = c;
+#pragma omp barrier
+#pragma omp single
+            for (int k = 0; k < nt; ++k) chunk_base[k + 1] += chunk_base[k];
+            uint32_t r = chunk_base[t];
+            for (size_t i = lo; i < hi; ++i)
+                if (is_first[i]) rank_of_item[i] = r++;
+        }
         remap.resize(d);
-        for (uint32_t r = 0; r < d; ++r) { remap[by_first[r].second] = r; res.first_index[r] = by_first[r].first; }
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+        for (int s = 0; s < kShards; ++s)
+            for (size_t l = 0; l < shard_first[s].size(); ++l) {
+                const uint32_t r = rank_of_item[shard_first[s][l]];
+                remap[shard_base[s] + l] = r;
+                res.first_index[r] = shard_first[s][l];
+            }
     } else {
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
         for (int s = 0; s < kShards; ++s)
             for (size_t l = 0; l < shard_first[s].size(); ++l) res.first_index[shard_base[s] + l] = shard_first[s][l];
     }
