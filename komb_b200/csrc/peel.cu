@@ -38,7 +38,7 @@ namespace {
 
 using namespace peel;
 
-constexpr unsigned long long kTraceWords = 16;   // words per round of the optional trace
+constexpr unsigned long long kTraceWords = 20;   // words per round of the optional trace
 
 union PeelShared {
     BlockShared cta;   // scan phase (both modes) and the CTA-wide process phase
@@ -123,7 +123,13 @@ __global__ void __launch_bounds__(kPeelThreads) peel_kernel(uint32_t n, const ui
         if (prof) {
             const unsigned long long tp4 = global_ns();
             st->prof_ns[2] += tp3 - tp2; st->prof_ns[3] += tp4 - tp3;
-            if (st->trace && trace_row < st->trace_cap) { st->trace[kTraceWords * trace_row + 4] = tp3 - tp2; st->trace[kTraceWords * trace_row + 5] = tp4 - tp3; }
+            if (st->trace && trace_row < st->trace_cap) {
+                unsigned long long *tr = st->trace + kTraceWords * trace_row;
+                tr[4] = tp3 - tp2; tr[5] = tp4 - tp3;
+                // cumulative counters over all CTAs (complete: every CTA added its share before the barrier)
+                tr[15] = *(volatile unsigned long long *)&st->batches; tr[16] = *(volatile unsigned long long *)&st->carried;
+                tr[17] = *(volatile unsigned long long *)&st->ring_pushed; tr[18] = *(volatile unsigned long long *)&st->shared;
+            }
         }
         // q_done == q_tail here and nothing moves until the next PROCESS phase
         if (__ldcg(&st->error)) break;
@@ -244,10 +250,10 @@ int peel_coreness(kombgpu_graph *g) {
         std::vector<unsigned long long> h(kTraceWords * rows);
         KG_CUDA(ctx, cudaMemcpy(h.data(), trace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE *f = fopen(trace_path, "w")) {
-            fprintf(f, "round,k,frontier,survivors,scan_ns,process_ns,wait_ns,scan_cyc_ids,scan_cyc_deg,scan_cyc_counters,scan_cyc_tail,p_init,p_first,p_lastdone,p_over,p_exit\n");
+            fprintf(f, "round,k,frontier,survivors,scan_ns,process_ns,wait_ns,scan_cyc_ids,scan_cyc_deg,scan_cyc_counters,scan_cyc_tail,p_init,p_first,p_lastdone,p_over,p_exit,cum_batches,cum_carried,cum_ring,cum_pool\n");
             for (uint32_t r = 0; r < rows; ++r) {
                 const unsigned long long *t = &h[kTraceWords * r];
-                fprintf(f, "%u,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", r, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], t[10], t[11], t[12], t[13], t[14]);
+                fprintf(f, "%u,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", r, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], t[10], t[11], t[12], t[13], t[14], t[15], t[16], t[17], t[18]);
             }
             fclose(f);
         }

@@ -62,6 +62,8 @@ struct PeelState {
     // CTA 0's view of where the time goes (ns): scan, barrier after scan, process, barrier after process
     unsigned long long prof_ns[4];
     unsigned long long batches;    // traversals over all CTAs
+    unsigned long long carried;    // warp mode: discoveries handed on in registers (followed cascades)
+    unsigned long long ring_pushed; // warp mode: discoveries and row pieces queued in a CTA's ring
     unsigned long long *trace;     // optional (KOMBGPU_TRACE): 6 words per round, CTA 0's view
     uint32_t trace_cap;
     uint32_t tune[8];              // warp mode knobs (peel_warp.cuh WarpTune): keep, wsplit, park_ns, thin, hub_slice

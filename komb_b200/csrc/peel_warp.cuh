@@ -60,6 +60,7 @@ struct WarpShared {
     uint32_t removed;
     uint32_t shared_cnt;
     uint32_t batches;
+    uint32_t carried, ring_pushed;
     uint32_t spare;
     long long t[6];       // CTA 0, trace only: entry, init done, first batch, last batch end, level over, exit
 };
@@ -269,7 +270,7 @@ __device__ __forceinline__ uint32_t warp_batch(const uint64_t ent, const uint32_
         }
         pos = __shfl_sync(kFullMask, pos, 0) + (inc - c);
         to_pool = __shfl_sync(kFullMask, to_pool, 0);
-        if (to_pool) n_shared += c;
+        if (to_pool) n_shared += c; else n_shared += c << 16;   // low half: to the pool, high half: to the ring (per batch < 65536)
 #pragma unroll
         for (int t = 0; t < kU; ++t) {
             if (!push[t]) continue;
@@ -427,7 +428,7 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
         if (prof) { sh.t[0] = clock64(); sh.t[2] = 0; sh.t[3] = 0; sh.t[4] = 0; }
         sh.r_head = 0; sh.r_tail = 0; sh.r_done = 0;
         sh.over = 0; sh.lock = 0; sh.credit = my_hi - my_lo; sh.gb = 0; sh.ge = 0; sh.polls = 0;
-        sh.removed = 0; sh.shared_cnt = 0; sh.batches = 0;
+        sh.removed = 0; sh.shared_cnt = 0; sh.batches = 0; sh.carried = 0; sh.ring_pushed = 0;
     }
     __syncthreads();
     if (my_hi > my_lo && tid < 32) {
@@ -447,7 +448,8 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
     tn.thin = st->tune[3];
     tn.hub_slice = st->tune[4];
     uint32_t rb = 0, re = 0;   // ring tickets this warp owns
-    uint32_t removed = 0, n_shared = 0, batches = 0;
+    uint32_t removed = 0, n_shared = 0, batches = 0, carried = 0;
+    uint32_t pool_cnt = 0, ring_cnt = 0;   // lane-local
     uint32_t spins = 0;
     unsigned long long idle_since = 0;  // lane 0
 
@@ -524,28 +526,36 @@ __device__ __forceinline__ uint32_t process_level_warp(const int32_t k, const ui
         while (n_carry) {   // follow the cascade this warp started; the tickets stay open (r_done) until it ends
             const uint64_t next = carry;
             const uint32_t n_next = n_carry;
+            carried += n_next;
             removed += warp_batch<kDist, kU>(next, n_next, k, row_ptr, col, deg, core_out, Q, cap, st, sh, part, tn, n_shared, carry, n_carry);
+            pool_cnt += n_shared & 0xffffu; ring_cnt += n_shared >> 16; n_shared = 0;
             ++batches;
         }
+        pool_cnt += n_shared & 0xffffu; ring_cnt += n_shared >> 16; n_shared = 0;
         __syncwarp();
         if (lane == 0) { __threadfence_block(); atomicAdd(&sh.r_done, m); if (prof) sh.t[3] = clock64(); }
     }
     if (prof && lane == 0 && sh.t[4] == 0) sh.t[4] = clock64();
-    n_shared = warp_reduce_add(n_shared);
+    pool_cnt = warp_reduce_add(pool_cnt);
+    ring_cnt = warp_reduce_add(ring_cnt);
     if (lane == 0) {
         if (removed) atomicAdd(&sh.removed, removed);
-        if (n_shared) atomicAdd(&sh.shared_cnt, n_shared);
+        if (pool_cnt) atomicAdd(&sh.shared_cnt, pool_cnt);
+        if (ring_cnt) atomicAdd(&sh.ring_pushed, ring_cnt);
+        if (carried) atomicAdd(&sh.carried, carried);
         atomicAdd(&sh.batches, batches);
     }
     __syncthreads();
     if (tid == 0) {
         if (sh.shared_cnt) atomicAdd(&st->shared, (unsigned long long)sh.shared_cnt);
         if (sh.batches) atomicAdd(&st->batches, (unsigned long long)sh.batches);
+        if (sh.carried) atomicAdd(&st->carried, (unsigned long long)sh.carried);
+        if (sh.ring_pushed) atomicAdd(&st->ring_pushed, (unsigned long long)sh.ring_pushed);
     }
     const uint32_t total_removed = sh.removed;
     if (prof && tid == 0) {
         sh.t[5] = clock64();
-        unsigned long long *tr = st->trace + 16ull * (round - 1);   // peel.cu: kTraceWords = 16, row = round - 1
+        unsigned long long *tr = st->trace + 20ull * (round - 1);   // peel.cu: kTraceWords = 20, row = round - 1
         if (round - 1 < st->trace_cap) {
             tr[10] = sh.t[1] - sh.t[0]; tr[11] = sh.t[2] ? sh.t[2] - sh.t[1] : 0; tr[12] = sh.t[3] ? sh.t[3] - sh.t[1] : 0;
             tr[13] = sh.t[4] - sh.t[1]; tr[14] = sh.t[5] - sh.t[1];
