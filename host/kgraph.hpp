@@ -16,6 +16,7 @@
 // (src/graph.cpp:58-61).
 #pragma once
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -87,9 +88,9 @@ inline char *put_u64(char *p, uint64_t v) {
     return p;
 }
 
-// format rows [lo, hi) with `fmt_row` into per-thread buffers, then write them in order
-template <typename RowFn>
-inline void write_rows(FILE *f, size_t n_rows, size_t max_row_bytes, int threads, RowFn fmt_row) {
+// format blocks of rows [lo, hi) with `fmt_block(p, lo, hi)` into per-thread buffers, then write them in order
+template <typename BlockFn>
+inline void write_row_blocks(FILE *f, size_t n_rows, size_t max_row_bytes, int threads, BlockFn fmt_block) {
     threads = std::max(1, threads);
     const size_t block = 1 << 16;
     std::vector<std::vector<char>> buf(threads);
@@ -100,13 +101,19 @@ inline void write_rows(FILE *f, size_t n_rows, size_t max_row_bytes, int threads
             size_t lo = base + block * t, hi = std::min(n_rows, lo + block);
             if (lo >= hi) continue;
             buf[t].resize((hi - lo) * max_row_bytes);
-            char *p = buf[t].data();
-            for (size_t i = lo; i < hi; ++i) p = fmt_row(p, i);
+            char *p = fmt_block(buf[t].data(), lo, hi);
             used[t] = (size_t)(p - buf[t].data());
         }
         for (int t = 0; t < threads; ++t)
             if (used[t]) fwrite(buf[t].data(), 1, used[t], f);
     }
+}
+template <typename RowFn>
+inline void write_rows(FILE *f, size_t n_rows, size_t max_row_bytes, int threads, RowFn fmt_row) {
+    write_row_blocks(f, n_rows, max_row_bytes, threads, [&](char *p, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) p = fmt_row(p, i);
+        return p;
+    });
 }
 
 class Kgraph {
@@ -119,7 +126,8 @@ class Kgraph {
     std::future<int> _ctx_ready;
     std::string _ctx_error;
     // results of the whole path, fetched in one overlapped call (kombgpu_graph_results) by readEdgeList
-    std::unique_ptr<PinnedArray<uint32_t>> _eu, _ev;
+    std::unique_ptr<PinnedArray<uint64_t>> _efp;   // edge list in CSR form: forward offsets per source + targets
+    std::unique_ptr<PinnedArray<uint32_t>> _ev;
     std::unique_ptr<PinnedArray<int32_t>> _deg, _core;
     std::unique_ptr<PinnedArray<double>> _score;
 
@@ -151,7 +159,7 @@ class Kgraph {
     }
     ~Kgraph() {
         if (_ctx_ready.valid()) _ctx_ready.wait();
-        _eu.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();  // pinned buffers go before the context
+        _efp.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();  // pinned buffers go before the context
         if (_graph) kombgpu_graph_destroy(_graph);
         if (_ctx) kombgpu_ctx_destroy(_ctx);
     }
@@ -184,7 +192,9 @@ class Kgraph {
     void getEdgeInfo(HitTable &hits) {
         timing_mark("tokenise SAMs");
         const size_t h = hits.tokens.keys.size();
-        InternResult keys = intern_spans(hits.tokens.keys, (int)_threads, false);
+        // ordered: ids follow first appearance, so the two mate files arrive as (at most) two runs of non-decreasing
+        // read ids and the device build merges them instead of radix-sorting the hits (build.cu, merge path)
+        InternResult keys = intern_spans(hits.tokens.keys, (int)_threads, true);
         hits.read_key.swap(keys.ids);
         // unitig ids: @SQ order first, then first appearance; only unitigs with a hit become vertices
         std::vector<Span> items;
@@ -225,19 +235,25 @@ class Kgraph {
         uint32_t n = 0;
         uint64_t m = 0;
         kombgpu_graph_counts(_graph, &n, &m);
-        // one call fetches everything the three output files need; the edge-list download overlaps the peel
-        _eu.reset(new PinnedArray<uint32_t>(_ctx, m));
+        // one call fetches everything the three output files need; the edge-list download (CSR form: offsets per
+        // source + targets, half the bytes of two id arrays) overlaps the peel
+        _efp.reset(new PinnedArray<uint64_t>(_ctx, (size_t)n + 1));
         _ev.reset(new PinnedArray<uint32_t>(_ctx, m));
         _deg.reset(new PinnedArray<int32_t>(_ctx, n));
         _core.reset(new PinnedArray<int32_t>(_ctx, n));
         _score.reset(new PinnedArray<double>(_ctx, n));
-        int rc = kombgpu_graph_results(_graph, _key_mode, _eu->data(), _ev->data(), _deg->data(), _core->data(), _score->data());
-        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_results", rc);
+        int rc = kombgpu_graph_results_csr(_graph, _key_mode, _efp->data(), _ev->data(), _deg->data(), _core->data(), _score->data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_results_csr", rc);
         timing_mark("pinned alloc + results");
-        PinnedArray<uint32_t> &u = *_eu, &v = *_ev;
-        write_rows(ef, m, 24, (int)_threads, [&](char *p, size_t i) {
-            p = put_u64(p, u[i]); *p++ = '\t';
-            p = put_u64(p, v[i]); *p++ = '\n';
+        const uint64_t *fp = _efp->data();
+        PinnedArray<uint32_t> &v = *_ev;
+        write_row_blocks(ef, m, 24, (int)_threads, [&](char *p, size_t lo, size_t hi) {
+            size_t u = (size_t)(std::upper_bound(fp, fp + n + 1, (uint64_t)lo) - fp) - 1;   // source of edge lo
+            for (size_t i = lo; i < hi; ++i) {
+                while (fp[u + 1] <= i) ++u;
+                p = put_u64(p, u); *p++ = '\t';
+                p = put_u64(p, v[i]); *p++ = '\n';
+            }
             return p;
         });
         fclose(ef);
@@ -297,7 +313,7 @@ class Kgraph {
             fclose(fp);
             timing_mark("write CoreA_anomaly.txt");
         }
-        _eu.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();
+        _efp.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();
         kombgpu_graph_destroy(_graph);
         _graph = nullptr;
         timing_mark("free pinned + graph");

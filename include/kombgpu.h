@@ -138,6 +138,16 @@ int kombgpu_graph_counts(const kombgpu_graph *g, uint32_t *n_vertices, uint64_t 
  * n_edges entries.  This is what the drop-in writes to edgelist.txt (quirk Q7). */
 int kombgpu_graph_edges(const kombgpu_graph *g, uint32_t *u, uint32_t *v);
 
+/* The same edge list in CSR form, half the bytes: edge i is (u, v[i]) for the u with
+ * fwd_ptr[u] <= i < fwd_ptr[u + 1]; fwd_ptr holds n_vertices + 1 entries, v holds n_edges. */
+int kombgpu_graph_edges_csr(const kombgpu_graph *g, uint64_t *fwd_ptr, uint32_t *v);
+
+/* Edge multiplicities, aligned with the canonical edge list: mult[i] = number of clique pairs (reads
+ * holding both unitigs; or duplicate input pairs for kombgpu_graph_from_edges) that collapsed into edge i.
+ * An extension: the reference drops duplicates without counting them (igraph_simplify with comb = NULL,
+ * src/graph.cpp:438); the sum over all edges equals kombgpu_stats.n_pairs minus the self-loops. */
+int kombgpu_graph_edge_multiplicity(const kombgpu_graph *g, uint32_t *mult);
+
 /* CSR of the symmetric graph: row_ptr[n+1], col[2E], every row ascending. */
 int kombgpu_graph_csr(const kombgpu_graph *g, uint64_t *row_ptr, uint32_t *col);
 
@@ -182,6 +192,11 @@ int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode);
 int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t *v, int32_t *degree,
                           int32_t *coreness, double *score);
 
+/* kombgpu_graph_results with the edge list in CSR form (see kombgpu_graph_edges_csr): n_vertices + 1
+ * offsets and n_edges targets instead of two arrays of n_edges -- half the device-to-host bytes. */
+int kombgpu_graph_results_csr(kombgpu_graph *g, int key_mode, uint64_t *fwd_ptr, uint32_t *v, int32_t *degree,
+                              int32_t *coreness, double *score);
+
 /* Densest k-core (needs kombgpu_coreness): the level k* whose core {v : coreness(v) >= k*} maximises
  * edges / vertices, with that block's size.  Bulk analogue of the greedy densest-block peel the reference keeps,
  * unreachable from main, in CombineCoreA::runMerge over HashIndexedMinHeap (src/CombineCoreA.h:45-219,
@@ -202,6 +217,11 @@ int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uint32_t *n_ve
 int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
                          uint32_t n_vertices, int key_mode, uint64_t edge_capacity, uint32_t *u, uint32_t *v,
                          int32_t *degree, int32_t *coreness, double *score, kombgpu_graph **out);
+
+/* kombgpu_analyse_hits with the edge list in CSR form: fwd_ptr[n_vertices + 1], v[edge_capacity]. */
+int kombgpu_analyse_hits_csr(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                             uint32_t n_vertices, int key_mode, uint64_t edge_capacity, uint64_t *fwd_ptr, uint32_t *v,
+                             int32_t *degree, int32_t *coreness, double *score, kombgpu_graph **out);
 
 int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out);
 
@@ -276,13 +296,6 @@ int kombgpu_corea_dev(kombgpu_ctx *ctx, const int32_t *coreness_dev, const int32
                       int key_mode, double *score_dev, double *max_score);
 
 int kombgpu_abi_version(void);
-
-/* Measurement aid (tools/sort_probe.py): sorts n synthetic 64-bit keys with lo_bits random low bits and
- * hi_bits bits at position 32 (random, or non-decreasing when sorted_hi != 0: the shape of hit arrays in
- * read order) on bits [0, lo_bits) + [32, 32 + hi_bits), `reps` times; returns the best time of the sort
- * alone and whether the result is a sorted permutation of the input.  Replaces nothing in the reference. */
-int kombgpu_debug_sort_u64(kombgpu_ctx *ctx, uint64_t n, int lo_bits, int hi_bits, int sorted_hi, int reps,
-                           float *ms_best, int *ok);
 
 #ifdef __cplusplus
 }

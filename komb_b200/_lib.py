@@ -31,7 +31,7 @@ class Stats(ctypes.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
-# every symbol include/kombgpu.h declares: name -> (restype, argtypes)
+# every symbol include/kombgpu.h and include/kombgpu_debug.h declare: name -> (restype, argtypes)
 u32p, u64p, i32p, f64p = POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32), POINTER(c_double)
 SIGNATURES = {
     "kombgpu_abi_version": (c_int, []),
@@ -54,6 +54,12 @@ SIGNATURES = {
     "kombgpu_graph_counts": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64)]),
     "kombgpu_graph_edges": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kombgpu_graph_csr": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kombgpu_graph_edges_csr": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kombgpu_graph_edge_multiplicity": (c_int, [c_void_p, c_void_p]),
+    "kombgpu_graph_results_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kombgpu_analyse_hits_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, POINTER(c_void_p)]),
+    "kombgpu_debug_peel_again": (c_int, [c_void_p]),
     "kombgpu_degree": (c_int, [c_void_p, c_void_p]),
     "kombgpu_coreness": (c_int, [c_void_p, c_void_p]),
     "kombgpu_corea": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p]),

@@ -114,6 +114,30 @@ class Context:
         return self._pair_call(self._lib.kombgpu_build_graph, self._lib.kombgpu_build_graph_dev,
                                read_key, unitig, int(n_vertices))
 
+    def analyse_hits_csr(self, read_key, unitig, n_vertices: int, key_mode: int = KEY_REF32, out: dict | None = None,
+                         edge_capacity: int | None = None) -> tuple["Graph", dict]:
+        """analyse_hits with the edge list in CSR form (kombgpu_analyse_hits_csr): result keys fwd_ptr (uint64[n+1])
+        and v (uint32[E]) instead of u and v -- half the device-to-host bytes."""
+        ha, hb = _host(read_key, np.uint32), _host(unitig, np.uint32)
+        if ha.shape != hb.shape or ha.ndim != 1:
+            raise ValueError("expected two 1-D arrays of equal length")
+        out = out or {}
+        n = int(n_vertices)
+        if out.get("v") is not None:
+            cap = out["v"].shape[0] if edge_capacity is None else int(edge_capacity)
+            bv = out["v"]
+        else:
+            cap = 3 * ha.shape[0] if edge_capacity is None else int(edge_capacity)
+            bv = np.empty(cap, np.uint32)
+        r = {"fwd_ptr": Graph._out(out.get("fwd_ptr"), n + 1, np.uint64), "degree": Graph._out(out.get("degree"), n, np.int32),
+             "coreness": Graph._out(out.get("coreness"), n, np.int32), "score": Graph._out(out.get("score"), n, np.float64)}
+        g = c_void_p()
+        self._check(self._lib.kombgpu_analyse_hits_csr(self._h, _ptr(ha), _ptr(hb), ha.shape[0], n, int(key_mode), cap, _ptr(r["fwd_ptr"]),
+                                                       _ptr(bv), _ptr(r["degree"]), _ptr(r["coreness"]), _ptr(r["score"]), byref(g)))
+        graph = Graph(self, g, None)
+        r["v"] = bv[:graph.counts()[1]]
+        return graph, r
+
     def analyse_hits(self, read_key, unitig, n_vertices: int, key_mode: int = KEY_REF32, out: dict | None = None,
                      edge_capacity: int | None = None) -> tuple["Graph", dict]:
         """Host hits in, every result on the host, one call (kombgpu_analyse_hits): the edge list starts downloading
@@ -209,6 +233,22 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_edges(self._h, _ptr(u), _ptr(v)))
         return u, v
 
+    def edges_csr(self, out=None) -> tuple[np.ndarray, np.ndarray]:
+        """Canonical edge list in CSR form: (fwd_ptr uint64[n+1], v uint32[E]); edge i has source u where
+        fwd_ptr[u] <= i < fwd_ptr[u+1] (kombgpu_graph_edges_csr)."""
+        n, m = self.counts()
+        fp = self._out(out[0] if out else None, n + 1, np.uint64)
+        v = self._out(out[1] if out else None, m, np.uint32)
+        self._ctx._check(self._lib.kombgpu_graph_edges_csr(self._h, _ptr(fp), _ptr(v)))
+        return fp, v
+
+    def edge_multiplicity(self) -> np.ndarray:
+        """Pairs that collapsed into each edge of the canonical edge list (kombgpu_graph_edge_multiplicity)."""
+        _, m = self.counts()
+        mult = np.empty(m, np.uint32)
+        self._ctx._check(self._lib.kombgpu_graph_edge_multiplicity(self._h, _ptr(mult)))
+        return mult
+
     def csr(self) -> tuple[np.ndarray, np.ndarray]:
         n, m = self.counts()
         row_ptr, col = np.empty(n + 1, np.uint64), np.empty(2 * m, np.uint32)
@@ -221,8 +261,12 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_degree(self._h, _ptr(d)))
         return d
 
-    def coreness(self, copy: bool = True, out=None):
+    def coreness(self, copy: bool = True, out=None, again: bool = False):
+        """igraph_coreness.  `again=True` (measurement aid, include/kombgpu_debug.h) peels once more on a graph that
+        already holds its coreness."""
         n, _ = self.counts()
+        if again:
+            self._ctx._check(self._lib.kombgpu_debug_peel_again(self._h))
         if not copy:
             self._ctx._check(self._lib.kombgpu_coreness(self._h, None))
             return None
@@ -250,6 +294,17 @@ class Graph:
              "score": self._out(out.get("score"), n, np.float64)}
         self._ctx._check(self._lib.kombgpu_graph_results(self._h, int(key_mode), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["degree"]),
                                                          _ptr(r["coreness"]), _ptr(r["score"])))
+        return r
+
+    def results_csr(self, key_mode: int = KEY_REF32, out: dict | None = None) -> dict:
+        """results() with the edge list in CSR form (fwd_ptr, v): half the download (kombgpu_graph_results_csr)."""
+        n, m = self.counts()
+        out = out or {}
+        r = {"fwd_ptr": self._out(out.get("fwd_ptr"), n + 1, np.uint64), "v": self._out(out.get("v"), m, np.uint32),
+             "degree": self._out(out.get("degree"), n, np.int32), "coreness": self._out(out.get("coreness"), n, np.int32),
+             "score": self._out(out.get("score"), n, np.float64)}
+        self._ctx._check(self._lib.kombgpu_graph_results_csr(self._h, int(key_mode), _ptr(r["fwd_ptr"]), _ptr(r["v"]), _ptr(r["degree"]),
+                                                             _ptr(r["coreness"]), _ptr(r["score"])))
         return r
 
     def analyse(self, key_mode: int = KEY_REF32):

@@ -255,6 +255,33 @@ struct EdgeFlagIn {
     }
 };
 
+// adjacent-unique of the sorted pair keys that also records how many pairs collapsed into each edge (the number of
+// reads supporting it: the "weight" of the north star's weighted graph; the reference itself keeps no weights,
+// src/graph.cpp:438 passes comb = NULL).  Runs are short (1.0005 pairs per edge on cfg2), so the head looks ahead a
+// few keys and only then falls back to a binary search for the end of its run.
+struct CompactEdgesMult {
+    const uint64_t *keys;
+    uint64_t n;
+    uint64_t *dst;
+    uint32_t *mult;
+    __device__ void operator()(uint64_t i, uint32_t pos, uint32_t flag) const {
+        if (!flag) return;
+        const uint64_t k = keys[i];
+        dst[pos] = k;
+        uint64_t r = 1;
+        while (r < 8 && i + r < n && keys[i + r] == k) ++r;
+        if (r == 8 && i + r < n && keys[i + r] == k) {
+            uint64_t lo = i + r, hi = n;   // first position past i + r whose key differs
+            while (lo < hi) {
+                const uint64_t mid = lo + (hi - lo) / 2;
+                if (keys[mid] == k) lo = mid + 1; else hi = mid;
+            }
+            r = lo - i;
+        }
+        mult[pos] = (uint32_t)r;
+    }
+};
+
 // ---- CSR ---------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kThreads) swap_pack_kernel(const uint64_t *__restrict__ edges, uint64_t n_edges,
@@ -436,6 +463,8 @@ int hits_to_sorted_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
     }
     const uint64_t *hits = other;  // unique hits grouped by read (sorted when the general path ran), n_uniq of them
     st->n_unique_hits = n_uniq;
+    // the segment scan below carries two 32-bit counters in one word whose top two bits are the scan's status flags
+    if (n_uniq >= (1u << 31)) return ctx_fail(ctx, KOMBGPU_EINVAL, "%u distinct (read, unitig) hits exceed the 2^31 per-device limit", n_uniq);
 
     // 2. reads with >= 2 unitigs -> segments; pairs per segment -> offsets
     DevBuf<uint32_t> seg_head, seg_tail;
@@ -503,10 +532,15 @@ int pairs_to_sorted_keys(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v,
 }  // namespace
 
 // sorted pair keys (duplicates, loops possible) -> unique simple edges
-int unique_edges(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, DevBuf<uint64_t> &edges, uint64_t *n_edges) {
+int unique_edges(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, DevBuf<uint64_t> &edges, uint64_t *n_edges,
+                 DevBuf<uint32_t> *mult) {
     DevBuf<uint32_t> d_count(ctx, 1);
     if (!d_count) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
     KG_ALLOC(ctx, edges, count);
+    if (mult) {
+        KG_ALLOC(ctx, *mult, count);
+        KG_TRY((device_scan<uint32_t>(ctx, count, EdgeFlagIn{keys}, CompactEdgesMult{keys, count, edges.p, mult->p}, d_count.p)));
+    } else
     KG_TRY((device_scan<uint32_t>(ctx, count, EdgeFlagIn{keys}, CompactKeysU64{keys, edges.p}, d_count.p)));
     uint32_t n32 = 0;
     KG_TRY(read_back(ctx, d_count.p, &n32, 1));
@@ -542,19 +576,27 @@ int lower_bounds_hi(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, cons
 }
 
 int hits_to_edges(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
-                  DevBuf<uint64_t> &edges, uint64_t *n_edges, kombgpu_stats *st) {
+                  DevBuf<uint64_t> &edges, uint64_t *n_edges, kombgpu_stats *st, DevBuf<uint32_t> *mult) {
     DevBuf<uint64_t> pa, pb;
     uint64_t *psorted = nullptr, n_pairs = 0;
     KG_TRY(hits_to_sorted_pairs(ctx, read_key, unitig, n_hits, n_vertices, pa, pb, &psorted, &n_pairs, st));
-    return unique_edges(ctx, psorted, n_pairs, edges, n_edges);
+    return unique_edges(ctx, psorted, n_pairs, edges, n_edges, mult);
 }
 
 int pairs_to_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
-                   DevBuf<uint64_t> &edges, uint64_t *n_edges) {
+                   DevBuf<uint64_t> &edges, uint64_t *n_edges, DevBuf<uint32_t> *mult) {
     DevBuf<uint64_t> ka, kb;
     uint64_t *sorted = nullptr;
     KG_TRY(pairs_to_sorted_keys(ctx, u, v, n_pairs, n_vertices, ka, kb, &sorted));
-    return unique_edges(ctx, sorted, n_pairs, edges, n_edges);
+    return unique_edges(ctx, sorted, n_pairs, edges, n_edges, mult);
+}
+
+int forward_index(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t E, uint32_t n, uint32_t **fwd_start_out) {
+    DevBuf<uint32_t> fwd_start;
+    KG_ALLOC(ctx, fwd_start, (size_t)n + 1);
+    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, edges, E, n, fwd_start.p);
+    *fwd_start_out = fwd_start.take();
+    return KOMBGPU_OK;
 }
 
 // unique simple edges (sorted, u < v) -> CSR of the symmetric graph
@@ -566,10 +608,10 @@ int csr_from_edges(kombgpu_ctx *ctx, DevBuf<uint64_t> &edges, uint64_t E, uint32
     DevBuf<uint64_t> sw_a, sw_b;
     uint64_t *swapped = nullptr;
     KG_TRY(swapped_sorted(ctx, edges.p, E, n, sw_a, sw_b, &swapped));
-    DevBuf<uint32_t> fwd_start, back_start;
-    KG_ALLOC(ctx, fwd_start, (size_t)n + 1);
+    DevBuf<uint32_t> back_start;
     KG_ALLOC(ctx, back_start, (size_t)n + 1);
-    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, edges.p, E, n, fwd_start.p);
+    if (!g->fwd_start) KG_TRY(forward_index(ctx, edges.p, E, n, &g->fwd_start));   // kept: the CSR form of the edge list
+    const uint32_t *fwd_start_p = g->fwd_start;
     KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, swapped, E, n, back_start.p);
 
     DevBuf<uint64_t> row_ptr;
@@ -580,13 +622,13 @@ int csr_from_edges(kombgpu_ctx *ctx, DevBuf<uint64_t> &edges, uint64_t E, uint32
     KG_ALLOC(ctx, col, 2 * E);
     if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
     KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
-    KG_TRY((device_scan<uint64_t>(ctx, n, DegreeIn{fwd_start.p, back_start.p}, DegreeOut{row_ptr.p, deg.p},
+    KG_TRY((device_scan<uint64_t>(ctx, n, DegreeIn{fwd_start_p, back_start.p}, DegreeOut{row_ptr.p, deg.p},
                                   (uint64_t *)nullptr)));
     if (n) KG_LAUNCH(ctx, reduce_max_i32_kernel, min(grid_for(n, kThreads), 148u * 8u), kThreads, 0, deg.p, (uint64_t)n, max_deg.p);
     KG_LAUNCH(ctx, set_u64_kernel, 1, 1, 0, row_ptr.p + n, 2 * E);
     if (E)
         KG_LAUNCH(ctx, fill_col_kernel, min(grid_for(E, kThreads), 148u * 16u), kThreads, 0, edges.p, swapped, E, row_ptr.p,
-                  fwd_start.p, back_start.p, col.p);
+                  fwd_start_p, back_start.p, col.p);
     KG_TRY(read_back(ctx, max_deg.p, &g->st.max_degree, 1));
     g->edges = edges.take();
     g->row_ptr = row_ptr.take();
@@ -673,7 +715,9 @@ int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uin
     DevBuf<uint64_t> edges;
     uint64_t E = 0;
     g->st.n_pairs = n_pairs;
-    KG_TRY(pairs_to_edges(ctx, u, v, n_pairs, n_vertices, edges, &E));
+    DevBuf<uint32_t> mult;
+    KG_TRY(pairs_to_edges(ctx, u, v, n_pairs, n_vertices, edges, &E, &mult));
+    g->mult = mult.take();
     return csr_from_edges(ctx, edges, E, n_vertices, g);
 }
 
@@ -681,7 +725,9 @@ int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *
                     uint32_t n_vertices, kombgpu_graph *g) {
     DevBuf<uint64_t> edges;
     uint64_t E = 0;
-    KG_TRY(hits_to_edges(ctx, read_key, unitig, n_hits, n_vertices, edges, &E, &g->st));
+    DevBuf<uint32_t> mult;
+    KG_TRY(hits_to_edges(ctx, read_key, unitig, n_hits, n_vertices, edges, &E, &g->st, &mult));
+    g->mult = mult.take();
     return csr_from_edges(ctx, edges, E, n_vertices, g);
 }
 
@@ -689,6 +735,9 @@ void graph_release(kombgpu_graph *g) {
     if (!g || !g->ctx) return;
     kombgpu_ctx *ctx = g->ctx;
     if (g->edges) ws_free(ctx, g->edges);
+    if (g->fwd_start) ws_free(ctx, g->fwd_start);
+    if (g->mult) ws_free(ctx, g->mult);
+    g->fwd_start = nullptr; g->mult = nullptr;
     if (g->row_ptr) ws_free(ctx, g->row_ptr);
     if (g->col) ws_free(ctx, g->col);
     if (g->deg) ws_free(ctx, g->deg);

@@ -5,6 +5,7 @@
 #include <new>
 
 #include "graph.cuh"
+#include "kombgpu_debug.h"
 
 namespace kg {
 namespace { __global__ void small_copy_kernel(const unsigned char *__restrict__ src, unsigned char *dst, uint32_t bytes); }
@@ -90,24 +91,16 @@ void ws_trim(kombgpu_ctx *ctx) {
 
 namespace {
 
+// stage timing with the context's own event pair (stages never nest)
 struct StageTimer {
     kombgpu_ctx *ctx;
-    cudaEvent_t a = nullptr, b = nullptr;
-    explicit StageTimer(kombgpu_ctx *c) : ctx(c) {
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
-        cudaEventRecord(a, ctx->stream);
-    }
+    explicit StageTimer(kombgpu_ctx *c) : ctx(c) { cudaEventRecord(ctx->ev_a, ctx->stream); }
     float stop() {
         float ms = 0.f;
-        cudaEventRecord(b, ctx->stream);
-        cudaEventSynchronize(b);
-        cudaEventElapsedTime(&ms, a, b);
+        cudaEventRecord(ctx->ev_b, ctx->stream);
+        cudaEventSynchronize(ctx->ev_b);
+        cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
         return ms;
-    }
-    ~StageTimer() {
-        cudaEventDestroy(a);
-        cudaEventDestroy(b);
     }
 };
 
@@ -137,6 +130,53 @@ __global__ void unpack_edges_kernel(const uint64_t *__restrict__ edges, uint64_t
         u[i] = (uint32_t)(e >> 32);
         v[i] = (uint32_t)e;
     }
+}
+
+// CSR form of the edge list: the targets alone (the sources are implied by the forward index)
+__global__ void edge_targets_kernel(const uint64_t *__restrict__ edges, uint64_t n_edges, uint32_t *__restrict__ v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += (uint64_t)gridDim.x * blockDim.x)
+        v[i] = (uint32_t)edges[i];
+}
+__global__ void widen_u32_kernel(const uint32_t *__restrict__ in, uint64_t count, uint64_t *__restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+// Start the download of the canonical edge list on the copy stream, behind everything queued on the compute stream so
+// far.  Pair form: u[E], v[E]; CSR form (fwd_ptr != nullptr): fwd_ptr[n + 1], v[E] -- half the bytes.
+// The staging buffers must stay alive until the copy stream has drained.
+struct EdgeDownload {
+    DevBuf<uint32_t> du, dv;
+    DevBuf<uint64_t> dptr;
+    bool in_flight = false;
+};
+int start_edge_download(kombgpu_ctx *ctx, const kombgpu_graph *g, const uint64_t *edges, uint64_t E, uint32_t n, uint32_t *u,
+                        uint64_t *fwd_ptr, uint32_t *v, EdgeDownload &dl) {
+    const uint32_t grid = min(ceil_div_u64(E ? E : 1, 256), (uint32_t)ctx->sm_count * 8u);
+    if (E) {
+        KG_ALLOC(ctx, dl.dv, E);
+        if (fwd_ptr) {
+            KG_LAUNCH(ctx, edge_targets_kernel, grid, 256, 0, edges, E, dl.dv.p);
+        } else {
+            KG_ALLOC(ctx, dl.du, E);
+            KG_LAUNCH(ctx, unpack_edges_kernel, grid, 256, 0, edges, E, dl.du.p, dl.dv.p);
+        }
+    }
+    if (fwd_ptr) {
+        KG_ALLOC(ctx, dl.dptr, (size_t)n + 1);
+        KG_LAUNCH(ctx, widen_u32_kernel, min(ceil_div_u64((uint64_t)n + 1, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->fwd_start,
+                  (uint64_t)n + 1, dl.dptr.p);
+    }
+    cudaEvent_t ready = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ready, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
+    dl.in_flight = true;
+    if (e == cudaSuccess && fwd_ptr) e = cudaMemcpyAsync(fwd_ptr, dl.dptr.p, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess && u && E) e = cudaMemcpyAsync(u, dl.du.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess && v && E) e = cudaMemcpyAsync(v, dl.dv.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (ready) cudaEventDestroy(ready);
+    if (e != cudaSuccess) return ctx_fail(ctx, KOMBGPU_ECUDA, "edge list download: %s", cudaGetErrorString(e));
+    return KOMBGPU_OK;
 }
 
 typedef int (*BuildFn)(kombgpu_ctx *, const uint32_t *, const uint32_t *, uint64_t, uint32_t, kombgpu_graph *);
@@ -220,6 +260,12 @@ int kombgpu_ctx_create(int device, kombgpu_ctx **out) {
         delete ctx;
         return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaStreamCreate failed");
     }
+    if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return ctx_fail(nullptr, KOMBGPU_ECUDA, "cudaEventCreate failed");
+    }
     ctx->pinned_bytes = 4096;
     if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
         ctx->pinned = nullptr;
@@ -236,6 +282,8 @@ void kombgpu_ctx_destroy(kombgpu_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->arena) cudaFree(b.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -371,7 +419,7 @@ int kombgpu_coreness(kombgpu_graph *g, int32_t *coreness) {
     if (!g) return KOMBGPU_EINVAL;
     kombgpu_ctx *ctx = g->ctx;
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!g->has_core || getenv("KOMBGPU_REPEEL")) {   // KOMBGPU_REPEEL: measurement aid, peel again on every call
+    if (!g->has_core) {
         const uint64_t launches0 = ctx->launches;
         StageTimer timer(ctx);
         int rc = peel_coreness(g);
@@ -383,11 +431,16 @@ int kombgpu_coreness(kombgpu_graph *g, int32_t *coreness) {
     return KOMBGPU_OK;
 }
 
+// measurement aid (include/kombgpu_debug.h): run the peel again on a graph that already has its coreness
+int kombgpu_debug_peel_again(kombgpu_graph *g) {
+    if (!g) return KOMBGPU_EINVAL;
+    g->has_core = false;
+    return kombgpu_coreness(g, nullptr);
+}
+
 int kombgpu_corea(kombgpu_ctx *ctx, const int32_t *coreness, const int32_t *degree, uint32_t n, int key_mode, double *score) {
     if (!ctx) return KOMBGPU_EINVAL;
     if (n && (!coreness || !degree || !score)) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
-    for (uint32_t i = 0; i < n; ++i)
-        if (coreness[i] < 0 || degree[i] < 0) return ctx_fail(ctx, KOMBGPU_EINVAL, "negative coreness/degree at %u", i);
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf<int32_t> dc, dd;
     DevBuf<double> ds;
@@ -434,48 +487,59 @@ int kombgpu_graph_analyse(kombgpu_graph *g, int key_mode) {
     return kombgpu_graph_corea(g, key_mode, nullptr);
 }
 
-int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t *v, int32_t *degree, int32_t *coreness,
-                          double *score) {
-    if (!g) return KOMBGPU_EINVAL;
+static int graph_results_impl(kombgpu_graph *g, int key_mode, uint32_t *u, uint64_t *fwd_ptr, uint32_t *v, int32_t *degree,
+                              int32_t *coreness, double *score) {
     kombgpu_ctx *ctx = g->ctx;
-    if ((u == nullptr) != (v == nullptr)) return ctx_fail(ctx, KOMBGPU_EINVAL, "u and v must be given together");
-    if (u && g->n_edges && !g->edges) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no canonical edge list");
+    const bool want_edges = v != nullptr;
+    if (want_edges && g->n_edges && !g->edges) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no canonical edge list");
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint64_t E = g->n_edges;
     const uint32_t n = g->n;
-    DevBuf<uint32_t> du, dv;  // live until the copy stream has drained
-    cudaEvent_t ready = nullptr;
+    EdgeDownload dl;   // staging lives until the copy stream has drained
     // 1. edge list + degree: final after the build -> start their download on the copy stream
-    if (u && E) {
-        KG_ALLOC(ctx, du, E);
-        KG_ALLOC(ctx, dv, E);
-        KG_LAUNCH(ctx, unpack_edges_kernel, min(ceil_div_u64(E, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->edges, E, du.p, dv.p);
+    int rc = KOMBGPU_OK;
+    if (want_edges) rc = start_edge_download(ctx, g, g->edges, g->n_edges, n, u, fwd_ptr, v, dl);
+    if (rc == KOMBGPU_OK && degree && n) {
+        cudaError_t e = cudaSuccess;
+        if (!dl.in_flight) {   // order the copy stream behind the build
+            cudaEvent_t ready = nullptr;
+            e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(ready, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
+            if (ready) cudaEventDestroy(ready);
+            dl.in_flight = true;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(degree, g->deg, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e != cudaSuccess) rc = ctx_fail(ctx, KOMBGPU_ECUDA, "results: %s", cudaGetErrorString(e));
     }
-    KG_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    cudaError_t e = cudaEventRecord(ready, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
-    if (e == cudaSuccess && u && E) e = cudaMemcpyAsync(u, du.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
-    if (e == cudaSuccess && v && E) e = cudaMemcpyAsync(v, dv.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
-    if (e == cudaSuccess && degree && n) e = cudaMemcpyAsync(degree, g->deg, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
-    cudaEventDestroy(ready);
-    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->copy_stream); return ctx_fail(ctx, KOMBGPU_ECUDA, "results: %s", cudaGetErrorString(e)); }
     // 2. peel + CORE-A on the compute stream meanwhile
-    int rc = kombgpu_coreness(g, nullptr);
+    if (rc == KOMBGPU_OK) rc = kombgpu_coreness(g, nullptr);
     if (rc == KOMBGPU_OK && (score || !g->has_score)) rc = kombgpu_graph_corea(g, key_mode, nullptr);
     if (rc == KOMBGPU_OK && coreness && n) rc = download(ctx, g->core, coreness, n);
     if (rc == KOMBGPU_OK && score && n) rc = download(ctx, g->score, score, n);
-    cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+    cudaError_t ce = dl.in_flight ? cudaStreamSynchronize(ctx->copy_stream) : cudaSuccess;
     if (rc != KOMBGPU_OK) return rc;
     if (ce != cudaSuccess) return ctx_fail(ctx, KOMBGPU_ECUDA, "results copy stream: %s", cudaGetErrorString(ce));
     return KOMBGPU_OK;
 }
 
-int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
-                         int key_mode, uint64_t edge_capacity, uint32_t *u, uint32_t *v, int32_t *degree, int32_t *coreness,
-                         double *score, kombgpu_graph **out) {
-    if (!ctx) return KOMBGPU_EINVAL;
+int kombgpu_graph_results(kombgpu_graph *g, int key_mode, uint32_t *u, uint32_t *v, int32_t *degree, int32_t *coreness,
+                          double *score) {
+    if (!g) return KOMBGPU_EINVAL;
+    if ((u == nullptr) != (v == nullptr)) return ctx_fail(g->ctx, KOMBGPU_EINVAL, "u and v must be given together");
+    return graph_results_impl(g, key_mode, u, nullptr, v, degree, coreness, score);
+}
+
+int kombgpu_graph_results_csr(kombgpu_graph *g, int key_mode, uint64_t *fwd_ptr, uint32_t *v, int32_t *degree, int32_t *coreness,
+                              double *score) {
+    if (!g) return KOMBGPU_EINVAL;
+    if ((fwd_ptr == nullptr) != (v == nullptr)) return ctx_fail(g->ctx, KOMBGPU_EINVAL, "fwd_ptr and v must be given together");
+    return graph_results_impl(g, key_mode, nullptr, fwd_ptr, v, degree, coreness, score);
+}
+
+static int analyse_hits_impl(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                             int key_mode, uint64_t edge_capacity, uint32_t *u, uint64_t *fwd_ptr, uint32_t *v, int32_t *degree,
+                             int32_t *coreness, double *score, kombgpu_graph **out) {
     if (!out || (n_hits && (!read_key || !unitig))) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
-    if ((u == nullptr) != (v == nullptr)) return ctx_fail(ctx, KOMBGPU_EINVAL, "u and v must be given together");
     *out = nullptr;
     if (n_vertices >= 0xfffffffeu) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_vertices too large");
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -484,10 +548,9 @@ int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
     g->ctx = ctx;
     g->st.max_coreness = -1;
     const uint64_t launches0 = ctx->launches;
-    DevBuf<uint32_t> du, dv;   // unpacked edge list: lives until the copy stream has drained
-    bool copies_in_flight = false;
+    EdgeDownload dl;   // staging of the edge list: lives until the copy stream has drained
     auto fail = [&](int rc) {
-        if (copies_in_flight) cudaStreamSynchronize(ctx->copy_stream);
+        if (dl.in_flight) cudaStreamSynchronize(ctx->copy_stream);
         graph_release(g);
         delete g;
         return rc;
@@ -500,26 +563,19 @@ int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
         if (rc == KOMBGPU_OK) rc = upload(ctx, db, unitig, n_hits);
         // stage 1a: the simple edge list (final here: the CSR only adds an index over it)
         DevBuf<uint64_t> edges;
+        DevBuf<uint32_t> mult;
         uint64_t E = 0;
-        if (rc == KOMBGPU_OK) rc = hits_to_edges(ctx, da.p, db.p, n_hits, n_vertices, edges, &E, &g->st);
-        if (rc == KOMBGPU_OK && u && E > edge_capacity)
+        if (rc == KOMBGPU_OK) rc = hits_to_edges(ctx, da.p, db.p, n_hits, n_vertices, edges, &E, &g->st, &mult);
+        g->mult = mult.take();
+        if (rc == KOMBGPU_OK && v && E > edge_capacity)
             rc = ctx_fail(ctx, KOMBGPU_EINVAL, "%llu edges do not fit the caller's edge buffers (%llu)", (unsigned long long)E,
                           (unsigned long long)edge_capacity);
+        if (rc == KOMBGPU_OK) rc = forward_index(ctx, edges.p, E, n_vertices, &g->fwd_start);
         if (rc != KOMBGPU_OK) return fail(rc);
         // its download starts now, on the copy stream, under the rest of the build, the peel and CORE-A
-        if (u && E) {
-            if (!du.alloc(ctx, E) || !dv.alloc(ctx, E)) return fail(ctx_fail(ctx, KOMBGPU_ENOMEM, "edge list staging"));
-            unpack_edges_kernel<<<min(ceil_div_u64(E, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(edges.p, E, du.p, dv.p);
-            ctx->launches++;
-            cudaEvent_t ready = nullptr;
-            cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventRecord(ready, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
-            copies_in_flight = true;
-            if (e == cudaSuccess) e = cudaMemcpyAsync(u, du.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(v, dv.p, E * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
-            if (ready) cudaEventDestroy(ready);
-            if (e != cudaSuccess) return fail(ctx_fail(ctx, KOMBGPU_ECUDA, "analyse_hits: %s", cudaGetErrorString(e)));
+        if (v) {
+            rc = start_edge_download(ctx, g, edges.p, E, n_vertices, u, fwd_ptr, v, dl);
+            if (rc != KOMBGPU_OK) return fail(rc);
         }
         // stage 1b: CSR
         rc = csr_from_edges(ctx, edges, E, n_vertices, g);
@@ -534,13 +590,53 @@ int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
     if (rc == KOMBGPU_OK && coreness && g->n) rc = download(ctx, g->core, coreness, g->n);
     if (rc == KOMBGPU_OK && score && g->n) rc = download(ctx, g->score, score, g->n);
     if (rc != KOMBGPU_OK) return fail(rc);
-    if (copies_in_flight) {
+    if (dl.in_flight) {
         cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
-        copies_in_flight = false;
+        dl.in_flight = false;
         if (ce != cudaSuccess) return fail(ctx_fail(ctx, KOMBGPU_ECUDA, "analyse_hits copy stream: %s", cudaGetErrorString(ce)));
     }
     *out = g;
     return KOMBGPU_OK;
+}
+
+int kombgpu_analyse_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                         int key_mode, uint64_t edge_capacity, uint32_t *u, uint32_t *v, int32_t *degree, int32_t *coreness,
+                         double *score, kombgpu_graph **out) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if ((u == nullptr) != (v == nullptr)) return ctx_fail(ctx, KOMBGPU_EINVAL, "u and v must be given together");
+    return analyse_hits_impl(ctx, read_key, unitig, n_hits, n_vertices, key_mode, edge_capacity, u, nullptr, v, degree, coreness, score, out);
+}
+
+int kombgpu_analyse_hits_csr(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                             int key_mode, uint64_t edge_capacity, uint64_t *fwd_ptr, uint32_t *v, int32_t *degree, int32_t *coreness,
+                             double *score, kombgpu_graph **out) {
+    if (!ctx) return KOMBGPU_EINVAL;
+    if ((fwd_ptr == nullptr) != (v == nullptr)) return ctx_fail(ctx, KOMBGPU_EINVAL, "fwd_ptr and v must be given together");
+    return analyse_hits_impl(ctx, read_key, unitig, n_hits, n_vertices, key_mode, edge_capacity, nullptr, fwd_ptr, v, degree, coreness, score, out);
+}
+
+int kombgpu_graph_edges_csr(const kombgpu_graph *g, uint64_t *fwd_ptr, uint32_t *v) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (!fwd_ptr || (g->n_edges && !v)) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    if (!g->fwd_start) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no canonical edge list");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    EdgeDownload dl;
+    int rc = start_edge_download(ctx, g, g->edges, g->n_edges, g->n, nullptr, fwd_ptr, v, dl);
+    cudaError_t ce = dl.in_flight ? cudaStreamSynchronize(ctx->copy_stream) : cudaSuccess;
+    if (rc != KOMBGPU_OK) return rc;
+    if (ce != cudaSuccess) return ctx_fail(ctx, KOMBGPU_ECUDA, "edge list download: %s", cudaGetErrorString(ce));
+    return KOMBGPU_OK;
+}
+
+int kombgpu_graph_edge_multiplicity(const kombgpu_graph *g, uint32_t *mult) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (g->n_edges && !mult) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    if (g->n_edges == 0) return KOMBGPU_OK;
+    if (!g->mult) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no edge multiplicities");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return download(ctx, g->mult, mult, g->n_edges);
 }
 
 int kombgpu_graph_stats(const kombgpu_graph *g, kombgpu_stats *out) {

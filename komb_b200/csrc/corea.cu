@@ -26,19 +26,23 @@ inline uint32_t grid_for(uint64_t n, int per_block, uint32_t cap) {
     return g < cap ? g : cap;
 }
 
-// mm[0] = max degree, mm[1] = max coreness
+// mm[0] = max degree, mm[1] = max coreness, mm[2] = 1 if any value is negative (input validation)
 __global__ void __launch_bounds__(kThreads) max2_kernel(const int32_t *__restrict__ deg, const int32_t *__restrict__ core,
                                                         uint32_t n, int32_t *__restrict__ mm) {
-    int32_t md = 0, mc = 0;
+    int32_t md = 0, mc = 0, lo = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        md = max(md, deg[i]);
-        mc = max(mc, core[i]);
+        const int32_t d = deg[i], c = core[i];
+        md = max(md, d);
+        mc = max(mc, c);
+        lo = min(lo, min(d, c));
     }
     md = warp_reduce_max(md);
     mc = warp_reduce_max(mc);
+    lo = warp_reduce_min(lo);
     if (lane_id() == 0) {
         if (md) atomicMax(&mm[0], md);
         if (mc) atomicMax(&mm[1], mc);
+        if (lo < 0) atomicExch(&mm[2], 1);
     }
 }
 
@@ -168,12 +172,13 @@ int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint
         return ctx_fail(ctx, KOMBGPU_EINVAL, "unknown CORE-A key mode %d", key_mode);
     const uint32_t cap = (uint32_t)ctx->sm_count * 8u;
 
-    DevBuf<int32_t> mm(ctx, 2);
+    DevBuf<int32_t> mm(ctx, 3);
     if (!mm) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_CUDA(ctx, cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    KG_CUDA(ctx, cudaMemsetAsync(mm.p, 0, 3 * sizeof(int32_t), ctx->stream));
     KG_LAUNCH(ctx, max2_kernel, grid_for(n, kThreads, cap), kThreads, 0, deg, core, n, mm.p);
-    int32_t h_mm[2] = {0, 0};
-    KG_TRY(read_back(ctx, mm.p, h_mm, 2));
+    int32_t h_mm[3] = {0, 0, 0};
+    KG_TRY(read_back(ctx, mm.p, h_mm, 3));
+    if (h_mm[2]) return ctx_fail(ctx, KOMBGPU_EINVAL, "negative coreness or degree");
     const uint32_t max_deg = (uint32_t)h_mm[0], max_core = (uint32_t)h_mm[1];
 
     // degree ranks through a histogram LUT

@@ -21,7 +21,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kSmemBins = 4096;
 
-// hist[core[v]] += 1 over vertices; hist[min(core[u], core[v])] += 1 over edges (when edges != nullptr)
+// kEdges = false: hist[core[v]] += 1 over the `count` vertices; kEdges = true: hist[min(core[u], core[v])] += 1 over the
+// `count` edges of the canonical edge list
+template <bool kEdges>
 __global__ void __launch_bounds__(kThreads) level_hist_kernel(const int32_t *__restrict__ core, const uint64_t *__restrict__ edges,
                                                               uint64_t count, uint32_t n_bins,
                                                               unsigned long long *__restrict__ hist) {
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) level_hist_kernel(const int32_t *__r
     }
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
         int32_t c;
-        if (edges) {
+        if (kEdges) {
             const uint64_t e = edges[i];
             c = min(core[(uint32_t)(e >> 32)], core[(uint32_t)e]);
         } else {
@@ -58,6 +60,7 @@ extern "C" int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uin
     if (!g) return KOMBGPU_EINVAL;
     kombgpu_ctx *ctx = g->ctx;
     if (!g->has_core) return ctx_fail(ctx, KOMBGPU_ESTATE, "kombgpu_graph_densest_core needs kombgpu_coreness first");
+    if (g->n_edges && !g->edges) return ctx_fail(ctx, KOMBGPU_ESTATE, "graph was adopted from a CSR: no canonical edge list");
     KG_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t best_k = 0;
     uint64_t best_v = g->n, best_e = g->n_edges;
@@ -68,9 +71,9 @@ extern "C" int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uin
         KG_ALLOC(ctx, hist, 2 * (size_t)n_bins);
         KG_CUDA(ctx, cudaMemsetAsync(hist.p, 0, 2 * (size_t)n_bins * sizeof(unsigned long long), ctx->stream));
         const uint32_t cap = (uint32_t)ctx->sm_count * 8u;
-        KG_LAUNCH(ctx, level_hist_kernel, min(ceil_div_u64(g->n, kThreads), cap), kThreads, 0, g->core, (const uint64_t *)nullptr,
+        KG_LAUNCH(ctx, level_hist_kernel<false>, min(ceil_div_u64(g->n, kThreads), cap), kThreads, 0, g->core, (const uint64_t *)nullptr,
                   (uint64_t)g->n, n_bins, hist.p);
-        KG_LAUNCH(ctx, level_hist_kernel, min(ceil_div_u64(g->n_edges, kThreads), cap), kThreads, 0, g->core, g->edges, g->n_edges,
+        KG_LAUNCH(ctx, level_hist_kernel<true>, min(ceil_div_u64(g->n_edges, kThreads), cap), kThreads, 0, g->core, g->edges, g->n_edges,
                   n_bins, hist.p + n_bins);
         std::vector<unsigned long long> h(2 * (size_t)n_bins);
         KG_TRY(read_back(ctx, hist.p, h.data(), h.size()));

@@ -11,6 +11,8 @@ struct kombgpu_graph {
     uint64_t *edges = nullptr;   // [E]   packed (u << 32 | v), u < v, ascending
     uint64_t *row_ptr = nullptr; // [n+1] CSR offsets of the symmetric graph
     uint32_t *col = nullptr;     // [2E]  neighbours, every row ascending
+    uint32_t *fwd_start = nullptr; // [n+1] forward index of the edge list: edges [fwd_start[u], fwd_start[u+1]) have source u
+    uint32_t *mult = nullptr;    // [E]   pairs (reads, or input duplicates) that support each edge
     int32_t *deg = nullptr;      // [n]
     int32_t *core = nullptr;     // [n]   after peel
     double *score = nullptr;     // [n]   after CORE-A
@@ -28,10 +30,13 @@ int build_from_pairs(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uin
                      kombgpu_graph *g);
 
 // building blocks of stage 1 shared with the partitioned (multi-GPU) path (build.cu)
+// `mult` (optional): receives, per unique edge, how many emitted pairs collapsed into it
 int hits_to_edges(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
-                  DevBuf<uint64_t> &edges, uint64_t *n_edges, kombgpu_stats *st);
+                  DevBuf<uint64_t> &edges, uint64_t *n_edges, kombgpu_stats *st, DevBuf<uint32_t> *mult = nullptr);
 int pairs_to_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices,
-                   DevBuf<uint64_t> &edges, uint64_t *n_edges);
+                   DevBuf<uint64_t> &edges, uint64_t *n_edges, DevBuf<uint32_t> *mult = nullptr);
+// fwd_start[x] = first edge whose source is >= x, x in [0, n]  (the edge list is sorted by source)
+int forward_index(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t n_edges, uint32_t n, uint32_t **fwd_start_out);
 int swapped_sorted(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t n_edges, uint32_t n_vertices, DevBuf<uint64_t> &a,
                    DevBuf<uint64_t> &b, uint64_t **out);
 int lower_bounds_hi(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, const uint32_t *bounds_host, int nb,

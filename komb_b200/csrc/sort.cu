@@ -13,6 +13,7 @@
 // and made every mix of the two slower (KOMBGPU_SORT_MATCH, measured 0/2/4/8 items).
 #include <cstdlib>
 
+#include "kombgpu_debug.h"
 #include "primitives.cuh"
 
 namespace kg {
@@ -394,15 +395,14 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
     if (n >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "radix_sort_u64: %llu keys exceed the 2^32 per-array limit", (unsigned long long)n);
     const char *sort_env = getenv("KOMBGPU_SORT");   // "legacy": the three-kernel passes (kept for A/B measurements)
     const bool legacy = n >= (1ull << 30) || n_passes > kMaxPasses || (sort_env && sort_env[0] == 'l');
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->sort_attr_set) {   // function attributes are per device: once per context, not per process
         KG_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
 #define KG_SWEEP_ATTR(BITS, MATCH) \
     KG_CUDA(ctx, cudaFuncSetAttribute(radix_sweep_kernel<BITS, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)))
         KG_SWEEP_ATTR(8, 8); KG_SWEEP_ATTR(0, 8); KG_SWEEP_ATTR(8, 4); KG_SWEEP_ATTR(0, 4);
         KG_SWEEP_ATTR(8, 2); KG_SWEEP_ATTR(0, 2); KG_SWEEP_ATTR(8, 0); KG_SWEEP_ATTR(0, 0);
 #undef KG_SWEEP_ATTR
-        attr_set = true;
+        ctx->sort_attr_set = true;
     }
     const uint32_t n_tiles = ceil_div_u64(n, kRsTile);
     uint64_t *src = a, *dst = b;

@@ -358,6 +358,94 @@ def test_results_one_call(ctx, oracle_mod):
         np.testing.assert_allclose(r2["score"], oracle_mod.corea(exp_core, exp_deg, oracle_mod.KEY_EXACT64), rtol=RTOL, atol=ATOL)
 
 
+def pair_multiplicity(rk, ut):
+    """numpy restatement: per read the set of unitigs (src/graph.cpp:259-285), every i<j pair (:332-347);
+    returns the canonical packed pairs that are not loops and how many reads emitted each."""
+    key = np.unique((rk.astype(np.uint64) << np.uint64(32)) | ut.astype(np.uint64))
+    r, u = key >> np.uint64(32), key & np.uint64(0xffffffff)
+    starts = np.flatnonzero(np.r_[True, r[1:] != r[:-1]])
+    ends = np.r_[starts[1:], len(r)]
+    out = []
+    for s, e in zip(starts.tolist(), ends.tolist()):
+        if e - s >= 2:
+            a = u[s:e]                                   # ascending: (a[i], a[j]), i<j is already (min, max)
+            iu, iv = np.triu_indices(e - s, 1)
+            out.append((a[iu] << np.uint64(32)) | a[iv])
+    allp = np.concatenate(out) if out else np.zeros(0, np.uint64)
+    return np.unique(allp, return_counts=True)
+
+
+def test_edge_list_csr_form_and_multiplicity(ctx, oracle_mod):
+    """kombgpu_graph_edges_csr / _results_csr / kombgpu_analyse_hits_csr give the canonical edge list as forward
+    offsets + targets; kombgpu_graph_edge_multiplicity counts the pairs behind every edge (extension X1)."""
+    n, n_pairs = 3000, 20000
+    m1, m2 = synth.metagenome_hits(n, n_pairs, seed=6)
+    rk = np.concatenate([m1.read_key, m2.read_key]); ut = np.concatenate([m1.unitig, m2.unitig])
+    exp_edges, exp_p, _ = oracle_mod.build_edges(rk, ut)
+    exp_deg, exp_core = oracle_mod.coreness(n, exp_edges)
+    pk, cnt = pair_multiplicity(rk, ut)
+    assert np.array_equal(pk, exp_edges) and int(cnt.sum()) == exp_p and cnt.max() > 1
+    with ctx.build_graph(rk, ut, n) as g:
+        fp, v = g.edges_csr()
+        assert fp.shape == (n + 1,) and fp[0] == 0 and fp[-1] == exp_edges.shape[0]
+        u = np.repeat(np.arange(n, dtype=np.uint32), np.diff(fp.astype(np.int64)))
+        assert np.array_equal(oracle_mod.pack_edges(u, v), exp_edges)
+        assert np.array_equal(g.edge_multiplicity(), cnt.astype(np.uint32))
+        r = g.results_csr()
+        assert np.array_equal(r["fwd_ptr"], fp) and np.array_equal(r["v"], v)
+        assert np.array_equal(r["degree"], exp_deg) and np.array_equal(r["coreness"], exp_core)
+    out = {"fwd_ptr": ctx.pinned_empty(n + 1, np.uint64), "v": ctx.pinned_empty(exp_edges.shape[0] + 7, np.uint32)}
+    g, r = ctx.analyse_hits_csr(rk, ut, n, oracle_mod.KEY_REF32, out=out)
+    with g:
+        assert np.array_equal(r["fwd_ptr"], fp) and np.array_equal(r["v"], v)
+        assert np.array_equal(r["coreness"], exp_core)
+        check_corea(oracle_mod, r["score"], exp_core, exp_deg, oracle_mod.KEY_REF32)
+    import komb_b200
+    with pytest.raises(komb_b200.KombGpuError):
+        ctx.analyse_hits_csr(rk, ut, n, edge_capacity=exp_edges.shape[0] - 1)
+    # duplicate input pairs of an edge list count as multiplicity; loops do not make edges
+    uu = np.array([0, 1, 0, 2, 2, 3], np.uint32); vv = np.array([1, 0, 1, 2, 3, 2], np.uint32)
+    with ctx.graph_from_edges(uu, vv, 4) as g:
+        eu, ev = g.edges()
+        assert list(zip(eu.tolist(), ev.tolist())) == [(0, 1), (2, 3)]
+        assert g.edge_multiplicity().tolist() == [3, 2]
+        fp2, v2 = g.edges_csr()
+        assert fp2.tolist() == [0, 1, 1, 2, 2] and v2.tolist() == [1, 3]
+
+
+def test_adopted_csr_has_no_edge_list(ctx):
+    """A graph adopted from a CSR holds no canonical edge list: every entry point that needs one says so
+    (KOMBGPU_ESTATE) instead of reading a null pointer."""
+    import torch
+    import komb_b200
+    row_ptr = torch.tensor([0, 2, 4, 6], dtype=torch.int64, device="cuda")
+    col = torch.tensor([1, 2, 0, 2, 0, 1], dtype=torch.int32, device="cuda")
+    with ctx.graph_from_csr(row_ptr, col, 3) as g:
+        assert g.coreness().tolist() == [2, 2, 2]
+        for call in (g.edges, g.edges_csr, g.edge_multiplicity, g.densest_core):
+            with pytest.raises(komb_b200.KombGpuError) as e:
+                call()
+            assert e.value.code == -5
+
+
+def test_two_contexts_in_one_process(oracle_mod):
+    """Function attributes (dynamic shared memory of the radix passes) are per device and are set per context."""
+    import torch
+    import komb_b200
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    u, v = synth.rmat_edges(14, 100000, n_vertices=9000, seed=2)
+    exp = oracle_mod.simplify(u, v)
+    ctxs = [komb_b200.Context(d) for d in devs]
+    try:
+        for c in ctxs:
+            with c.graph_from_edges(u, v, 9000) as g:
+                gu, gv = g.edges()
+                assert np.array_equal(oracle_mod.pack_edges(gu, gv), exp)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def komb_b200_key_exact():
     import komb_b200
     return komb_b200.KEY_EXACT64

@@ -103,9 +103,9 @@ def test_large_random_sam_many_threads(tmp_path, oracle_mod):
 
 
 def test_c_abi_exports_every_declared_symbol():
-    """include/kombgpu.h <-> libkombgpu.so <-> the ctypes table (no compute call without a GPU)."""
+    """include/*.h <-> libkombgpu.so <-> the ctypes table (no compute call without a GPU)."""
     from komb_b200 import _lib
-    header = (ROOT / "include" / "kombgpu.h").read_text()
+    header = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))
     declared = set(re.findall(r"\b(kombgpu_[a-z_0-9]+)\s*\(", header))
     assert declared == set(_lib.SIGNATURES)
     lib = _lib.load()

@@ -3,12 +3,11 @@
     python tools/peel_ab.py [cfg2] [rmat22] [ramp] [rmat24d]
 
 For each graph: peel with the CTA-wide process phase (reference result + time), then the warp-autonomous
-one under several knob settings; every result is compared with the first.  Uses KOMBGPU_REPEEL so that one
+one under several knob settings; every result is compared with the first.  Uses Graph.coreness(again=True) so that one
 graph is peeled many times."""
 import os, sys, time, json
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-os.environ["KOMBGPU_REPEEL"] = "1"
 import numpy as np
 import komb_b200
 from komb_b200 import synth
@@ -68,7 +67,7 @@ def main():
             ok = True
             try:
                 for _ in range(reps):
-                    core = g.coreness()
+                    core = g.coreness(again=True)
                     st = g.stats()
                     best = min(best, st["ms_peel_kernel"])
                     if ref is None:
