@@ -295,6 +295,91 @@ int kombgpu_part_peel_apply_dev(kombgpu_part *part, int32_t k, const uint32_t *r
 int kombgpu_corea_dev(kombgpu_ctx *ctx, const int32_t *coreness_dev, const int32_t *degree_dev, uint32_t n,
                       int key_mode, double *score_dev, double *max_score);
 
+
+/* ---- multi-GPU, peer-memory path: the whole hot path over the GPUs of one node -------------------------------
+ *
+ * One rank per GPU (one process per rank, or one host thread per rank inside one process).  The graph is
+ * partitioned by unitig-id range: rank q owns ids [q * step, (q + 1) * step), step = ceil(n / world).  Ranks talk
+ * through peer memory over NVLink / NVSwitch (a symmetric heap mapped with cudaIpc between processes, direct peer
+ * access inside a process); no collective library is called on this path.
+ *
+ *   build   every rank turns ITS reads' hits into clique pairs, stores each pair straight into the receive buffer
+ *           of the rank that owns min(u, v); the owner sorts + deduplicates, sends the reversed copy of every edge
+ *           to the owner of max(u, v), and both halves become the owner's CSR rows
+ *   peel    one persistent kernel per GPU; decrements of unitigs another rank owns travel as messages written
+ *           into that rank's mailbox; ranks meet once per cascade generation through flags in peer memory
+ *   CORE-A  degree ranks from the summed degree histograms, key ranks from the merged lists of distinct keys
+ *
+ * This replaces the same reference calls as the single-GPU entry points (src/komb2.cpp:104-132). */
+typedef struct kombgpu_comm kombgpu_comm;
+typedef struct kombgpu_dist_graph kombgpu_dist_graph;
+
+/* Bootstrap: all-gather `bytes_per_rank` bytes from every rank into `recv` (rank order), blocking, returns 0 on
+ * success.  The only service the host has to provide (MPI_Allgather, torch.distributed.all_gather, ...); used
+ * to exchange memory handles when the symmetric heap grows, never on the data path. */
+typedef int (*kombgpu_allgather_fn)(void *user, const void *send, void *recv, uint64_t bytes_per_rank);
+
+/* Collective over all ranks.  `heap_bytes`: size of a symmetric-heap segment (0 = 512 MiB); the heap grows by
+ * segments as needed and is reused across calls.  Every rank must sit on its own GPU of one node. */
+int kombgpu_comm_create(kombgpu_ctx *ctx, int rank, int world, kombgpu_allgather_fn allgather, void *user,
+                        uint64_t heap_bytes, kombgpu_comm **out);
+/* The ranks of ONE process: call from `world` host threads, one per rank, each with its own context, all passing
+ * the address of the same pointer variable (initially NULL) as `group_slot`; the bootstrap is built in.  Ranks on
+ * distinct GPUs use peer access; all ranks on one GPU is accepted as an emulation mode for tests (the ranks then
+ * never wait for one another on the device: exchanges are done by the host threads and the peel runs every rank's
+ * share inside one cooperative grid). */
+int kombgpu_comm_create_local(kombgpu_ctx *ctx, int rank, int world, void **group_slot, uint64_t heap_bytes,
+                              kombgpu_comm **out);
+void kombgpu_comm_destroy(kombgpu_comm *comm);
+/* A rank of a one-process group whose host code failed: the ranks waiting for it in a collective return
+ * KOMBGPU_ESTATE instead of waiting for ever.  (Between processes a missing rank trips the 30 s watchdogs.) */
+int kombgpu_comm_abort(kombgpu_comm *comm);
+int kombgpu_comm_info(const kombgpu_comm *comm, int *rank, int *world, int *same_device, uint64_t *heap_bytes);
+
+typedef struct kombgpu_dist_stats {
+    uint64_t n_hits_local;      /* hits this rank passed in                                     */
+    uint64_t n_pairs_local;     /* clique pairs this rank emitted (or pairs passed in)          */
+    uint64_t n_pairs_received;  /* pairs routed to this rank (before dedup)                     */
+    uint64_t n_fwd_local;       /* edges (u < v) whose u this rank owns                         */
+    uint64_t n_directed_local;  /* CSR entries of the local rows                                */
+    uint64_t n_edges_global;    /* E                                                            */
+    uint64_t n_messages_sent;   /* peel: decrements sent to other ranks                         */
+    uint64_t n_messages_recv;   /* peel: decrements received                                    */
+    uint32_t n_global, v_lo, n_local;
+    int32_t max_degree;         /* global                                                       */
+    int32_t max_coreness;       /* global, -1 before the peel                                   */
+    uint32_t peel_levels;       /* non-empty levels                                             */
+    uint32_t peel_subrounds;    /* cross-rank exchange steps of the peel (all levels)           */
+    uint32_t peel_solo_subrounds; /* of those, run by one CTA per GPU (thin cascades)           */
+    float ms_build, ms_peel, ms_corea;   /* CUDA-event times on this rank                       */
+    float ms_build_route, ms_build_sort, ms_build_csr;
+} kombgpu_dist_stats;
+
+/* Stage 1..3 over all ranks, collective.  Inputs are device pointers on the rank's device: the hits of THIS
+ * rank's reads (both mates, global unitig ids; a read's hits must all be on one rank), or this rank's share of an
+ * edge list.  Results stay on the device until fetched. */
+int kombgpu_dist_build_hits_dev(kombgpu_comm *comm, const uint32_t *read_key_dev, const uint32_t *unitig_dev,
+                                uint64_t n_hits, uint32_t n_vertices_global, kombgpu_dist_graph **out);
+int kombgpu_dist_build_pairs_dev(kombgpu_comm *comm, const uint32_t *u_dev, const uint32_t *v_dev, uint64_t n_pairs,
+                                 uint32_t n_vertices_global, kombgpu_dist_graph **out);
+int kombgpu_dist_coreness(kombgpu_dist_graph *g);               /* igraph_coreness over all ranks */
+int kombgpu_dist_corea(kombgpu_dist_graph *g, int key_mode);    /* CoreA::getAnomalyScore over all ranks */
+void kombgpu_dist_graph_destroy(kombgpu_dist_graph *g);
+
+int kombgpu_dist_graph_stats(const kombgpu_dist_graph *g, kombgpu_dist_stats *out);
+/* This rank's slice to the host: degree / coreness / score of unitigs [v_lo, v_lo + n_local); any pointer may be
+ * NULL. */
+int kombgpu_dist_graph_results(const kombgpu_dist_graph *g, int32_t *degree, int32_t *coreness, double *score);
+/* This rank's slice of the canonical edge list (the slices of ranks 0, 1, ... concatenate to the global sorted
+ * list): u[n_fwd_local], v[n_fwd_local], mult[n_fwd_local]; any pointer may be NULL. */
+int kombgpu_dist_graph_edges(const kombgpu_dist_graph *g, uint32_t *u, uint32_t *v, uint32_t *mult);
+/* Device pointers of the rank's arrays (valid until destroy); any out-pointer may be NULL. */
+int kombgpu_dist_graph_device_arrays(const kombgpu_dist_graph *g, const uint64_t **row_ptr, const uint32_t **col,
+                                     const uint64_t **edges_packed, const int32_t **degree, const int32_t **coreness,
+                                     const double **score);
+/* Global scalars of CombineCoreA::run: max coreness and max CORE-A score (every rank gets the same values). */
+int kombgpu_dist_graph_summary(const kombgpu_dist_graph *g, int32_t *max_coreness, double *max_score);
+
 int kombgpu_abi_version(void);
 
 #ifdef __cplusplus

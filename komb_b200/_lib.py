@@ -31,6 +31,25 @@ class Stats(ctypes.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class DistStats(ctypes.Structure):
+    """struct kombgpu_dist_stats"""
+    _fields_ = [
+        ("n_hits_local", c_uint64), ("n_pairs_local", c_uint64), ("n_pairs_received", c_uint64), ("n_fwd_local", c_uint64),
+        ("n_directed_local", c_uint64), ("n_edges_global", c_uint64), ("n_messages_sent", c_uint64), ("n_messages_recv", c_uint64),
+        ("n_global", c_uint32), ("v_lo", c_uint32), ("n_local", c_uint32),
+        ("max_degree", c_int32), ("max_coreness", c_int32), ("peel_levels", c_uint32), ("peel_subrounds", c_uint32),
+        ("peel_solo_subrounds", c_uint32),
+        ("ms_build", c_float), ("ms_peel", c_float), ("ms_corea", c_float),
+        ("ms_build_route", c_float), ("ms_build_sort", c_float), ("ms_build_csr", c_float),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# bootstrap all-gather callback of kombgpu_comm_create
+ALLGATHER_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_uint64)
+
 # every symbol include/kombgpu.h and include/kombgpu_debug.h declare: name -> (restype, argtypes)
 u32p, u64p, i32p, f64p = POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32), POINTER(c_double)
 SIGNATURES = {
@@ -88,6 +107,22 @@ SIGNATURES = {
     "kombgpu_part_outbox_route_dev": (c_int, [c_void_p, POINTER(c_uint32), c_int, c_void_p, POINTER(c_uint64)]),
     "kombgpu_part_peel_apply_dev": (c_int, [c_void_p, c_int32, c_void_p, c_uint64, POINTER(c_uint32)]),
     "kombgpu_corea_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p, POINTER(c_double)]),
+    # multi-GPU, peer-memory path
+    "kombgpu_comm_create": (c_int, [c_void_p, c_int, c_int, ALLGATHER_FN, c_void_p, c_uint64, POINTER(c_void_p)]),
+    "kombgpu_comm_create_local": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_uint64, POINTER(c_void_p)]),
+    "kombgpu_comm_destroy": (None, [c_void_p]),
+    "kombgpu_comm_abort": (c_int, [c_void_p]),
+    "kombgpu_comm_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_uint64)]),
+    "kombgpu_dist_build_hits_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_dist_build_pairs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_dist_coreness": (c_int, [c_void_p]),
+    "kombgpu_dist_corea": (c_int, [c_void_p, c_int]),
+    "kombgpu_dist_graph_destroy": (None, [c_void_p]),
+    "kombgpu_dist_graph_stats": (c_int, [c_void_p, POINTER(DistStats)]),
+    "kombgpu_dist_graph_results": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kombgpu_dist_graph_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kombgpu_dist_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
+    "kombgpu_dist_graph_summary": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_double)]),
 }
 
 _lib = None

@@ -400,7 +400,7 @@ struct AnyHeadFlag {  // unique of sorted directed entries (no loop test: routed
 // hits -> all clique pairs, sorted (duplicates still in).  pa / pb are the ping-pong buffers.
 int hits_to_sorted_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
                          uint32_t n_vertices, DevBuf<uint64_t> &pa, DevBuf<uint64_t> &pb, uint64_t **psorted_out,
-                         uint64_t *n_pairs_out, kombgpu_stats *st) {
+                         uint64_t *n_pairs_out, kombgpu_stats *st, bool sort_pairs = true) {
     if (n_hits >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_hits >= 2^32 is not supported on one device");
     const int bn = bits_for(n_vertices > 0 ? n_vertices - 1 : 0);
     st->n_hits = n_hits;
@@ -488,7 +488,7 @@ int hits_to_sorted_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
 
     // 3. emit all pairs, sort
     KG_ALLOC(ctx, pa, n_pairs);
-    KG_ALLOC(ctx, pb, n_pairs);
+    if (sort_pairs) KG_ALLOC(ctx, pb, n_pairs);
     uint64_t *psorted = pa.p;
     if (n_pairs) {
         const uint32_t n_tiles = ceil_div_u64(n_pairs, kEmitTile);
@@ -497,8 +497,10 @@ int hits_to_sorted_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint3
         KG_LAUNCH(ctx, emit_partition_kernel, grid_for(n_tiles, kThreads), kThreads, 0, seg_base.p, n_seg, n_tiles, tile_seg.p);
         KG_LAUNCH(ctx, emit_pairs_kernel, n_tiles, kThreads, 0, hits, seg_head.p, seg_base.p, n_seg, tile_seg.p, n_tiles,
                   n_pairs, pa.p);
-        int npp = plan_radix_passes(0, bn, 32, 32 + bn, passes);
-        KG_TRY(radix_sort_u64(ctx, pa.p, pb.p, n_pairs, passes, npp, &psorted));
+        if (sort_pairs) {
+            int npp = plan_radix_passes(0, bn, 32, 32 + bn, passes);
+            KG_TRY(radix_sort_u64(ctx, pa.p, pb.p, n_pairs, passes, npp, &psorted));
+        }
     }
     *psorted_out = psorted;
     return KOMBGPU_OK;
@@ -589,6 +591,29 @@ int pairs_to_edges(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint6
     uint64_t *sorted = nullptr;
     KG_TRY(pairs_to_sorted_keys(ctx, u, v, n_pairs, n_vertices, ka, kb, &sorted));
     return unique_edges(ctx, sorted, n_pairs, edges, n_edges, mult);
+}
+
+// hits -> every clique pair as a canonical key (min << 32 | max), in emission order (not sorted, duplicates in)
+int hits_to_pairs(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_vertices,
+                  DevBuf<uint64_t> &pairs, uint64_t *n_pairs, kombgpu_stats *st) {
+    DevBuf<uint64_t> unused;
+    uint64_t *p = nullptr;
+    return hits_to_sorted_pairs(ctx, read_key, unitig, n_hits, n_vertices, pairs, unused, &p, n_pairs, st, false);
+}
+
+// (u, v) pairs -> canonical keys (min << 32 | max), input order; ids are range-checked
+int pairs_to_keys(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_vertices, DevBuf<uint64_t> &keys) {
+    if (n_pairs >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "n_pairs >= 2^32 is not supported on one device");
+    DevBuf<uint32_t> info(ctx, 2);
+    KG_ALLOC(ctx, keys, n_pairs);
+    if (!info) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    if (n_pairs)
+        KG_LAUNCH(ctx, pack_pairs_kernel, min(grid_for(n_pairs, kThreads), 148u * 16u), kThreads, 0, u, v, n_pairs, n_vertices, keys.p, info.p);
+    uint32_t h_info[2] = {0, 0};
+    KG_TRY(read_back(ctx, info.p, h_info, 2));
+    if (h_info[1]) return ctx_fail(ctx, KOMBGPU_EINVAL, "edge endpoint >= n_vertices (%u)", n_vertices);
+    return KOMBGPU_OK;
 }
 
 int forward_index(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t E, uint32_t n, uint32_t **fwd_start_out) {

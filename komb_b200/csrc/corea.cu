@@ -11,7 +11,9 @@
 // Ranks are exact half-integers in FP64 (class [s, e) of the ascending order has
 // descending average rank n - (s + e - 1) / 2); only ln() can differ from glibc,
 // by <= 1 ulp, far inside the 1e-6 relative tolerance the path is held to.
-#include "graph.cuh"
+#include <cstring>
+
+#include "dgraph.cuh"
 #include "primitives.cuh"
 
 namespace kg {
@@ -80,10 +82,11 @@ struct RankLutOut {
 };
 
 // sort key: high word orders the vertices by CORE-A key, low word = vertex id
+// (`count` elements; `n` is the vertex count of the WHOLE graph, which enters the reference's key arithmetic)
 __global__ void __launch_bounds__(kThreads) pack_rank_keys_kernel(const int32_t *__restrict__ core,
-                                                                  const int32_t *__restrict__ deg, uint32_t n, int mode,
+                                                                  const int32_t *__restrict__ deg, uint32_t count, uint32_t n, int mode,
                                                                   int deg_bits, uint64_t *__restrict__ keys) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t hi;
         if (mode == 0) {
             // (int32)(coreness * n + degree) with two's complement wrap; flip the sign bit for unsigned order
@@ -199,19 +202,19 @@ int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint
     RadixPass passes[8];
     int wide = 0;
     if (key_mode == KOMBGPU_KEY_REF32) {
-        KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, 0, 0, ka.p);
+        KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, n, 0, 0, ka.p);
         int np = plan_radix_passes(32, 64, 0, 0, passes);
         KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n, passes, np, &sorted));
     } else {
         const int db = bits_for(max_deg), cb = bits_for(max_core);
         if (db + cb <= 32) {
-            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, 1, db, ka.p);
+            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, n, 1, db, ka.p);
             int np = plan_radix_passes(32, 32 + db + cb, 0, 0, passes);
             KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n, passes, np, &sorted));
         } else {
             // (coreness, degree) does not fit 32 bits: LSD over the two fields with a re-key in between
             wide = 1;
-            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, 2, 0, ka.p);
+            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, n, 2, 0, ka.p);
             int np = plan_radix_passes(32, 32 + db, 0, 0, passes);
             KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n, passes, np, &sorted));
             uint64_t *other = sorted == ka.p ? kb.p : ka.p;
@@ -235,6 +238,214 @@ int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint
     unsigned long long h_bits = 0;
     KG_TRY(read_back(ctx, max_bits.p, &h_bits, 1));
     memcpy(max_score_host, &h_bits, sizeof(double));
+    return KOMBGPU_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// CORE-A over the ranks of a communicator: every rank scores its own unitigs.
+//   degree ranks   the degree histograms of all ranks are summed (each rank reads its peers' histograms from
+//                  peer memory), then the same prefix scan -> LUT as on one GPU
+//   key ranks      a rank sorts ITS keys and turns them into a list of distinct keys with their first positions;
+//                  the global rank of a key class is n - (2 * less + equal - 1) / 2 with less / equal summed over
+//                  the ranks' lists by binary search -- the lists are tiny next to the vertex arrays (distinct
+//                  (coreness, degree) pairs), so nothing of size n ever crosses a link
+// Ranks are exact half-integers as before; the result does not depend on the partition.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(kThreads) sum_peer_hist_kernel(PeerPtrs<uint32_t> hist, int world, uint32_t n_bins,
+                                                                 uint32_t *__restrict__ total) {
+    for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_bins; d += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t s = 0;
+        for (int q = 0; q < world; ++q) s += hist.p[q][d];
+        total[d] = s;
+    }
+}
+
+// distinct key of every class of the locally sorted sequence, as a 64-bit value that orders like the sort did
+__global__ void __launch_bounds__(kThreads) class_keys_kernel(const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ head_pos,
+                                                              uint32_t n_classes, const int32_t *__restrict__ core,
+                                                              const int32_t *__restrict__ deg, uint32_t n_global, int key_mode,
+                                                              uint64_t *__restrict__ dkey, uint32_t *__restrict__ dhead) {
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_classes; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h = head_pos[c];
+        const uint32_t v = (uint32_t)sorted[h];
+        dkey[c] = key_mode == KOMBGPU_KEY_REF32 ? (uint64_t)(((uint32_t)core[v] * n_global + (uint32_t)deg[v]) ^ 0x80000000u)
+                                                : (((uint64_t)(uint32_t)core[v] << 32) | (uint32_t)deg[v]);
+        dhead[c] = h;
+    }
+}
+
+struct ClassLists {
+    const uint64_t *key[kMaxRanks];
+    const uint32_t *head[kMaxRanks];
+    uint32_t n_classes[kMaxRanks];
+    uint32_t n_local[kMaxRanks];
+};
+
+// global descending average rank of every local class
+__global__ void __launch_bounds__(kThreads) class_rank_kernel(ClassLists L, int world, int rank, uint32_t n_global,
+                                                              double *__restrict__ class_rank) {
+    const uint32_t n_mine = L.n_classes[rank];
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_mine; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = L.key[rank][c];
+        uint64_t less = 0, eq = 0;
+        for (int q = 0; q < world; ++q) {
+            const uint32_t dq = L.n_classes[q];
+            uint32_t lo = 0, hi = dq;   // first class of rank q whose key is >= x
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (L.key[q][mid] < x) lo = mid + 1; else hi = mid;
+            }
+            const uint32_t at = lo < dq ? L.head[q][lo] : L.n_local[q];
+            less += at;
+            if (lo < dq && L.key[q][lo] == x) eq += (lo + 1 < dq ? L.head[q][lo + 1] : L.n_local[q]) - at;
+        }
+        // ascending positions [less, less + eq) of the global order -> descending ranks, mean n - (2 less + eq - 1) / 2
+        class_rank[c] = (double)n_global - 0.5 * (double)(2 * less + eq - 1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) dist_score_kernel(const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ cls,
+                                                              const double *__restrict__ class_rank, const int32_t *__restrict__ deg,
+                                                              const double *__restrict__ deg_lut, uint32_t n_local,
+                                                              double *__restrict__ score, unsigned long long *__restrict__ max_bits) {
+    double local_max = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = (uint32_t)sorted[i];
+        const double sc = fabs(log(deg_lut[deg[v]]) - log(class_rank[cls[i]]));
+        score[v] = sc;
+        local_max = fmax(local_max, sc);
+    }
+    unsigned long long bits = (unsigned long long)__double_as_longlong(local_max);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(kFullMask, bits, o);
+        bits = t > bits ? t : bits;
+    }
+    if (lane_id() == 0 && bits) atomicMax(max_bits, bits);
+}
+
+}  // namespace
+
+int dist_corea(kombgpu_dist_graph *g, int key_mode) {
+    kombgpu_comm *c = g->comm;
+    kombgpu_ctx *ctx = g->ctx;
+    const int world = c->world;
+    const uint32_t n_local = g->n_local, n = g->n_global;
+    if (key_mode != KOMBGPU_KEY_REF32 && key_mode != KOMBGPU_KEY_EXACT64)
+        return ctx_fail(ctx, KOMBGPU_EINVAL, "unknown CORE-A key mode %d", key_mode);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    KG_CUDA(ctx, cudaEventCreate(&ev0));
+    KG_CUDA(ctx, cudaEventCreate(&ev1));
+    KG_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    if (!g->score) {
+        g->score = static_cast<double *>(ws_alloc(ctx, (n_local ? n_local : 1) * sizeof(double)));
+        if (!g->score) return ctx_fail(ctx, KOMBGPU_ENOMEM, "score array");
+    }
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8u;
+    const uint32_t max_deg = (uint32_t)g->st.max_degree, max_core = (uint32_t)(g->st.max_coreness > 0 ? g->st.max_coreness : 0);
+    const SymMark mark = sym_mark(c);
+
+    // ---- degree ranks: sum of the ranks' histograms -> LUT
+    const uint32_t n_bins = max_deg + 1;
+    uint32_t *hist = nullptr;
+    PeerPtrs<uint32_t> hist_peers{};
+    KG_TRY(sym_alloc(c, (size_t)n_bins, &hist, &hist_peers));
+    KG_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)n_bins * sizeof(uint32_t), ctx->stream));
+    if (n_local) KG_LAUNCH(ctx, degree_hist_kernel, grid_for(n_local, kThreads * 8, cap), kThreads, 0, g->deg, n_local, n_bins, hist);
+
+    // ---- local key order (same kernels as the single-GPU path, keys built with the GLOBAL n)
+    DevBuf<uint64_t> ka, kb;
+    KG_ALLOC(ctx, ka, n_local);
+    KG_ALLOC(ctx, kb, n_local);
+    uint64_t *sorted = ka.p;
+    RadixPass passes[8];
+    int wide = 0;
+    if (n_local) {
+        if (key_mode == KOMBGPU_KEY_REF32) {
+            KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n_local, kThreads, cap), kThreads, 0, g->core, g->deg, n_local, n, 0, 0, ka.p);
+            int np = plan_radix_passes(32, 64, 0, 0, passes);
+            KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n_local, passes, np, &sorted));
+        } else {
+            const int db = bits_for(max_deg), cb = bits_for(max_core);
+            if (db + cb <= 32) {
+                KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n_local, kThreads, cap), kThreads, 0, g->core, g->deg, n_local, n, 1, db, ka.p);
+                int np = plan_radix_passes(32, 32 + db + cb, 0, 0, passes);
+                KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n_local, passes, np, &sorted));
+            } else {
+                wide = 1;
+                KG_LAUNCH(ctx, pack_rank_keys_kernel, grid_for(n_local, kThreads, cap), kThreads, 0, g->core, g->deg, n_local, n, 2, 0, ka.p);
+                int np = plan_radix_passes(32, 32 + db, 0, 0, passes);
+                KG_TRY(radix_sort_u64(ctx, ka.p, kb.p, n_local, passes, np, &sorted));
+                uint64_t *other = sorted == ka.p ? kb.p : ka.p;
+                KG_LAUNCH(ctx, rekey_by_core_kernel, grid_for(n_local, kThreads, cap), kThreads, 0, g->core, n_local, sorted);
+                np = plan_radix_passes(32, 32 + cb, 0, 0, passes);
+                uint64_t *sorted2 = sorted;
+                KG_TRY(radix_sort_u64(ctx, sorted, other, n_local, passes, np, &sorted2));
+                sorted = sorted2;
+            }
+        }
+    }
+    DevBuf<uint32_t> head_pos, cls, d_classes(ctx, 1);
+    KG_ALLOC(ctx, head_pos, n_local);
+    KG_ALLOC(ctx, cls, n_local);
+    if (!d_classes) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_TRY((device_scan<uint32_t>(ctx, n_local, ClassFlagIn{sorted, g->core, g->deg, wide}, ClassFlagOut{head_pos.p, cls.p}, d_classes.p)));
+    uint32_t n_classes = 0;
+    KG_TRY(read_back(ctx, d_classes.p, &n_classes, 1));
+
+    // ---- publish the list of distinct keys; meet; rank the local classes against every rank's list
+    unsigned long long mine[2] = {n_classes, n_local}, all[kMaxRanks * 2];
+    KG_TRY(comm_exchange(c, mine, 2, all));   // also: every rank's histogram is complete
+    uint32_t max_classes = 1;
+    ClassLists L{};
+    for (int q = 0; q < world; ++q) {
+        L.n_classes[q] = (uint32_t)all[q * 2];
+        L.n_local[q] = (uint32_t)all[q * 2 + 1];
+        if (L.n_classes[q] > max_classes) max_classes = L.n_classes[q];
+    }
+    uint64_t *dkey = nullptr;
+    uint32_t *dhead = nullptr;
+    PeerPtrs<uint64_t> dkey_peers{};
+    PeerPtrs<uint32_t> dhead_peers{};
+    KG_TRY(sym_alloc(c, (size_t)max_classes, &dkey, &dkey_peers));
+    KG_TRY(sym_alloc(c, (size_t)max_classes, &dhead, &dhead_peers));
+    if (n_classes)
+        KG_LAUNCH(ctx, class_keys_kernel, grid_for(n_classes, kThreads, cap), kThreads, 0, sorted, head_pos.p, n_classes, g->core, g->deg, n,
+                  key_mode, dkey, dhead);
+    DevBuf<uint32_t> hist_total;
+    DevBuf<double> lut, class_rank;
+    KG_ALLOC(ctx, hist_total, n_bins);
+    KG_ALLOC(ctx, lut, n_bins);
+    KG_ALLOC(ctx, class_rank, n_classes);
+    KG_LAUNCH(ctx, sum_peer_hist_kernel, grid_for(n_bins, kThreads, cap), kThreads, 0, hist_peers, world, n_bins, hist_total.p);
+    KG_TRY((device_scan<uint32_t>(ctx, n_bins, HistIn{hist_total.p}, RankLutOut{lut.p, n}, (uint32_t *)nullptr)));
+    unsigned long long token = 1, tokens[kMaxRanks];
+    KG_TRY(comm_exchange(c, &token, 1, tokens));   // every rank's list is in place
+    for (int q = 0; q < world; ++q) { L.key[q] = dkey_peers.p[q]; L.head[q] = dhead_peers.p[q]; }
+    if (n_classes)
+        KG_LAUNCH(ctx, class_rank_kernel, grid_for(n_classes, kThreads, cap), kThreads, 0, L, world, c->rank, n, class_rank.p);
+    DevBuf<unsigned long long> max_bits(ctx, 1);
+    if (!max_bits) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(max_bits.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (n_local)
+        KG_LAUNCH(ctx, dist_score_kernel, grid_for(n_local, kThreads, cap), kThreads, 0, sorted, cls.p, class_rank.p, g->deg, lut.p, n_local,
+                  g->score, max_bits.p);
+    unsigned long long h_bits = 0, all_bits[kMaxRanks];
+    KG_TRY(read_back(ctx, max_bits.p, &h_bits, 1));
+    KG_TRY(comm_exchange(c, &h_bits, 1, all_bits));   // also: nobody releases lists a peer is still reading
+    sym_release(c, mark);
+    unsigned long long gmax = 0;
+    for (int q = 0; q < world; ++q) gmax = all_bits[q] > gmax ? all_bits[q] : gmax;
+    memcpy(&g->max_score, &gmax, sizeof(double));
+    g->has_score = true;
+    KG_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+    KG_CUDA(ctx, cudaEventSynchronize(ev1));
+    cudaEventElapsedTime(&g->st.ms_corea, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
     return KOMBGPU_OK;
 }
 
