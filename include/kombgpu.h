@@ -373,6 +373,9 @@ int kombgpu_dist_graph_results(const kombgpu_dist_graph *g, int32_t *degree, int
 /* This rank's slice of the canonical edge list (the slices of ranks 0, 1, ... concatenate to the global sorted
  * list): u[n_fwd_local], v[n_fwd_local], mult[n_fwd_local]; any pointer may be NULL. */
 int kombgpu_dist_graph_edges(const kombgpu_dist_graph *g, uint32_t *u, uint32_t *v, uint32_t *mult);
+/* The same slice in CSR form: fwd_ptr[n_local + 1] (edge i has source v_lo + x where fwd_ptr[x] <= i < fwd_ptr[x+1])
+ * and v[n_fwd_local]. */
+int kombgpu_dist_graph_edges_csr(const kombgpu_dist_graph *g, uint64_t *fwd_ptr, uint32_t *v);
 /* Device pointers of the rank's arrays (valid until destroy); any out-pointer may be NULL. */
 int kombgpu_dist_graph_device_arrays(const kombgpu_dist_graph *g, const uint64_t **row_ptr, const uint32_t **col,
                                      const uint64_t **edges_packed, const int32_t **degree, const int32_t **coreness,

@@ -121,6 +121,7 @@ SIGNATURES = {
     "kombgpu_dist_graph_stats": (c_int, [c_void_p, POINTER(DistStats)]),
     "kombgpu_dist_graph_results": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "kombgpu_dist_graph_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kombgpu_dist_graph_edges_csr": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kombgpu_dist_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
     "kombgpu_dist_graph_summary": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_double)]),
 }

@@ -17,6 +17,10 @@ __global__ void unpack_local_edges_kernel(const uint64_t *__restrict__ edges, ui
     }
 }
 
+__global__ void widen_local_kernel(const uint32_t *__restrict__ in, uint64_t count, uint64_t *__restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
 template <typename T>
 int fetch(kombgpu_ctx *ctx, const T *dev, T *host, size_t count) {
     if (!host || count == 0) return KOMBGPU_OK;
@@ -109,6 +113,26 @@ int kombgpu_dist_graph_edges(const kombgpu_dist_graph *g, uint32_t *u, uint32_t 
         KG_TRY(fetch(ctx, dv.p, v, m));
     }
     return fetch(ctx, g->mult, mult, m);
+}
+
+int kombgpu_dist_graph_edges_csr(const kombgpu_dist_graph *g, uint64_t *fwd_ptr, uint32_t *v) {
+    if (!g) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = g->ctx;
+    if (!fwd_ptr || (g->n_fwd && !v)) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t m = g->n_fwd;
+    DevBuf<uint32_t> dv;
+    DevBuf<uint64_t> dp;
+    KG_ALLOC(ctx, dp, (size_t)g->n_local + 1);
+    KG_LAUNCH(ctx, widen_local_kernel, min(ceil_div_u64((uint64_t)g->n_local + 1, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->fwd_start,
+              (uint64_t)g->n_local + 1, dp.p);
+    if (m) {
+        KG_ALLOC(ctx, dv, m);
+        KG_LAUNCH(ctx, unpack_local_edges_kernel, min(ceil_div_u64(m, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->edges, m,
+                  (uint32_t *)nullptr, dv.p);
+    }
+    KG_TRY(fetch(ctx, dp.p, fwd_ptr, (size_t)g->n_local + 1));
+    return fetch(ctx, dv.p, v, m);
 }
 
 int kombgpu_dist_graph_device_arrays(const kombgpu_dist_graph *g, const uint64_t **row_ptr, const uint32_t **col,

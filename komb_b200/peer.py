@@ -147,6 +147,15 @@ class DistGraph:
                                                             c_void_p(mult.ctypes.data) if with_mult else None))
         return (u, v, mult) if with_mult else (u, v)
 
+    def edges_csr(self, out: dict | None = None):
+        """This rank's slice of the edge list as (fwd_ptr uint64[n_local+1], v uint32[n_fwd_local])."""
+        st = self.stats()
+        out = out or {}
+        fp = out.get("fwd_ptr", np.empty(st["n_local"] + 1, np.uint64))[:st["n_local"] + 1]
+        v = out.get("v", np.empty(st["n_fwd_local"], np.uint32))[:st["n_fwd_local"]]
+        self._ctx._check(self._lib.kombgpu_dist_graph_edges_csr(self._h, c_void_p(fp.ctypes.data), c_void_p(v.ctypes.data)))
+        return fp, v
+
     def device_arrays(self) -> dict:
         ptrs = [c_void_p() for _ in range(6)]
         self._ctx._check(self._lib.kombgpu_dist_graph_device_arrays(self._h, *[byref(p) for p in ptrs]))
