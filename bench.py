@@ -642,10 +642,7 @@ def run_ours_multi(args, rank, world, local_rank):
         g.close()
         return st
 
-    n_loc = N_UNITIGS
-    pin = {"fwd_ptr": ctx.pinned_empty(n_loc + 1, np.uint64), "v": ctx.pinned_empty(int(2.2 * rk_h.numel()), np.uint32),
-           "coreness": ctx.pinned_empty(n_loc, np.int32), "degree": ctx.pinned_empty(n_loc, np.int32),
-           "score": ctx.pinned_empty(n_loc, np.float64)}
+    pin = {}
 
     def step_e2e():
         """Host hits in, this rank's share of every output back on the host (edge-list slice in CSR form, degree,
@@ -660,7 +657,12 @@ def run_ours_multi(args, rank, world, local_rank):
 
     n_warm = 1 if args.profile else max(args.warmup, 3)
     for _ in range(n_warm):
-        step_device()
+        st_w = step_device()
+    # page-locked result buffers, sized from the warm-up (a rank's share of the edge list depends on the id range it owns)
+    n_loc = st_w["n_local"]
+    pin.update({"fwd_ptr": ctx.pinned_empty(n_loc + 1, np.uint64), "v": ctx.pinned_empty(st_w["n_fwd_local"] + 1024, np.uint32),
+                "coreness": ctx.pinned_empty(n_loc, np.int32), "degree": ctx.pinned_empty(n_loc, np.int32),
+                "score": ctx.pinned_empty(n_loc, np.float64)})
     launches0 = ctx.launches()
     sampler = ClockSampler(local_rank)
     sampler.start()

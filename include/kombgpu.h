@@ -306,8 +306,9 @@ int kombgpu_corea_dev(kombgpu_ctx *ctx, const int32_t *coreness_dev, const int32
  *   build   every rank turns ITS reads' hits into clique pairs, stores each pair straight into the receive buffer
  *           of the rank that owns min(u, v); the owner sorts + deduplicates, sends the reversed copy of every edge
  *           to the owner of max(u, v), and both halves become the owner's CSR rows
- *   peel    one persistent kernel per GPU; decrements of unitigs another rank owns travel as messages written
- *           into that rank's mailbox; ranks meet once per cascade generation through flags in peer memory
+ *   peel    one persistent kernel per GPU; a rank logs the unitigs it peels and copies the new part of its log into
+ *           every peer (4 bytes per peeled unitig cross a link, whatever its degree); every rank decrements ITS
+ *           neighbours of each logged unitig; ranks meet once per cascade generation through flags in peer memory
  *   CORE-A  degree ranks from the summed degree histograms, key ranks from the merged lists of distinct keys
  *
  * This replaces the same reference calls as the single-GPU entry points (src/komb2.cpp:104-132). */
@@ -343,14 +344,14 @@ typedef struct kombgpu_dist_stats {
     uint64_t n_fwd_local;       /* edges (u < v) whose u this rank owns                         */
     uint64_t n_directed_local;  /* CSR entries of the local rows                                */
     uint64_t n_edges_global;    /* E                                                            */
-    uint64_t n_messages_sent;   /* peel: decrements sent to other ranks                         */
-    uint64_t n_messages_recv;   /* peel: decrements received                                    */
+    uint64_t n_messages_sent;   /* peel: unitig ids this rank copied into peers' logs           */
+    uint64_t n_messages_recv;   /* peel: unitig ids other ranks logged here                     */
     uint32_t n_global, v_lo, n_local;
     int32_t max_degree;         /* global                                                       */
     int32_t max_coreness;       /* global, -1 before the peel                                   */
     uint32_t peel_levels;       /* non-empty levels                                             */
     uint32_t peel_subrounds;    /* cross-rank exchange steps of the peel (all levels)           */
-    uint32_t peel_solo_subrounds; /* of those, run by one CTA per GPU (thin cascades)           */
+    uint32_t peel_solo_subrounds; /* of those, walked by one CTA on this GPU (thin cascades)    */
     float ms_build, ms_peel, ms_corea;   /* CUDA-event times on this rank                       */
     float ms_build_route, ms_build_sort, ms_build_csr;
 } kombgpu_dist_stats;
@@ -376,7 +377,8 @@ int kombgpu_dist_graph_edges(const kombgpu_dist_graph *g, uint32_t *u, uint32_t 
 /* The same slice in CSR form: fwd_ptr[n_local + 1] (edge i has source v_lo + x where fwd_ptr[x] <= i < fwd_ptr[x+1])
  * and v[n_fwd_local]. */
 int kombgpu_dist_graph_edges_csr(const kombgpu_dist_graph *g, uint64_t *fwd_ptr, uint32_t *v);
-/* Device pointers of the rank's arrays (valid until destroy); any out-pointer may be NULL. */
+/* Device pointers of the rank's arrays (valid until destroy); any out-pointer may be NULL.  row_ptr / col come
+ * back NULL: a rank keeps its adjacency grouped by neighbour for the peel, not as CSR rows. */
 int kombgpu_dist_graph_device_arrays(const kombgpu_dist_graph *g, const uint64_t **row_ptr, const uint32_t **col,
                                      const uint64_t **edges_packed, const int32_t **degree, const int32_t **coreness,
                                      const double **score);

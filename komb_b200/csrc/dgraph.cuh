@@ -18,8 +18,11 @@ struct kombgpu_dist_graph {
     uint64_t *edges = nullptr;     // [n_fwd]  (u << 32 | v), global ids, ascending
     uint32_t *mult = nullptr;      // [n_fwd]
     uint32_t *fwd_start = nullptr; // [n_local + 1]
-    uint64_t *row_ptr = nullptr;   // [n_local + 1]
-    uint32_t *col = nullptr;       // [n_directed] global ids; row = [neighbours < v (any order) | neighbours > v ascending]
+    // the local entries of the symmetric adjacency, grouped by NEIGHBOUR: for every unitig x of the whole graph,
+    // nbr[nbr_ptr[x] .. nbr_ptr[x + 1]) are the LOCAL ids (u - v_lo) of the unitigs this rank owns that are adjacent to x.
+    // (By symmetry this is the transpose of the rank's rows: when x is peeled, these are the degrees this rank decrements.)
+    uint32_t *nbr_ptr = nullptr;   // [n_global + 1]
+    uint32_t *nbr = nullptr;       // [n_directed]
     int32_t *deg = nullptr;        // [n_local]
     int32_t *core = nullptr;       // [n_local] after the peel
     double *score = nullptr;       // [n_local] after CORE-A

@@ -8,7 +8,8 @@
 //                 bucketing and sending are one pass, and every pair is sorted exactly once, by its owner
 //   owner         radix sort + adjacent-unique (+ multiplicities) -> its slice of the canonical edge list
 //   route 2       (v - v_lo(owner(v))) << 32 | u of every edge goes to the owner of v
-//   owner         stable sort of what arrived on the row bits -> backward half of its rows; CSR assembly
+//   owner         forward and backward entries together, keyed by the NEIGHBOUR and sorted on it: for every unitig x of
+//                 the graph the list of local unitigs adjacent to x -- the form the partitioned peel walks (ppeel.cu)
 // The only host round trips are the two count exchanges (the receive sizes have to be known to allocate).
 #include "dgraph.cuh"
 #include "primitives.cuh"
@@ -148,49 +149,42 @@ __global__ void __launch_bounds__(kThreads) row_bounds_checked_kernel(const uint
     }
 }
 
-struct PDegreeIn {
-    const uint32_t *fwd_start;
-    const uint32_t *back_start;
-    __device__ uint64_t operator()(uint64_t v) const {
-        return (uint64_t)(fwd_start[v + 1] - fwd_start[v]) + (uint64_t)(back_start[v + 1] - back_start[v]);
-    }
-};
-struct PDegreeOut {
-    uint64_t *row_ptr;
-    int32_t *deg;
-    __device__ void operator()(uint64_t v, uint64_t prefix, uint64_t d) const {
-        row_ptr[v] = prefix;
-        deg[v] = (int32_t)d;
-    }
-};
-
-// row x = [back neighbours (smaller ids) | forward neighbours (larger ids, ascending)]
-__global__ void __launch_bounds__(kThreads) pfill_fwd_kernel(const uint64_t *__restrict__ edges, uint64_t n_fwd, uint32_t base,
-                                                             const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ fwd_start,
-                                                             const uint32_t *__restrict__ back_start, uint32_t *__restrict__ col) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fwd; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t e = edges[i];
-        const uint32_t x = (uint32_t)(e >> 32) - base;
-        col[row_ptr[x] + (back_start[x + 1] - back_start[x]) + (i - fwd_start[x])] = (uint32_t)e;
-    }
-}
-__global__ void __launch_bounds__(kThreads) pfill_back_kernel(const uint64_t *__restrict__ back, uint64_t n_back,
-                                                              const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ back_start,
-                                                              uint32_t *__restrict__ col) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_back; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = back[i];
-        const uint32_t x = (uint32_t)(s >> 32);   // local row (rebased by the route)
-        col[row_ptr[x] + (i - back_start[x])] = (uint32_t)s;
+// the local adjacency entries keyed by the neighbour: entry i < n_fwd is the forward edge (u, v) -> (v << 32 | u - v_lo);
+// entry n_fwd + j is arrival j ((u - v_lo) << 32 | w) -> (w << 32 | u - v_lo), and counts one backward neighbour of u
+__global__ void __launch_bounds__(kThreads) nbr_keys_kernel(const uint64_t *__restrict__ edges, uint64_t n_fwd, const uint64_t *__restrict__ back,
+                                                            uint64_t n_back, uint32_t v_lo, uint32_t n_local, uint32_t n_global,
+                                                            uint64_t *__restrict__ keys, int32_t *__restrict__ back_cnt, uint32_t *__restrict__ err) {
+    const uint64_t total = n_fwd + n_back;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i < n_fwd) {
+            const uint64_t e = edges[i];
+            keys[i] = ((uint64_t)(uint32_t)e << 32) | (uint64_t)((uint32_t)(e >> 32) - v_lo);
+        } else {
+            const uint64_t s = back[i - n_fwd];
+            const uint32_t u = (uint32_t)(s >> 32), w = (uint32_t)s;
+            if (u >= n_local || w >= n_global) { atomicExch(err, 2u); keys[i] = 0; continue; }   // a mis-routed entry must not write past the arrays
+            keys[i] = ((uint64_t)w << 32) | u;
+            atomicAdd(&back_cnt[u], 1);
+        }
     }
 }
 
-__global__ void __launch_bounds__(kThreads) pmax_i32_kernel(const int32_t *__restrict__ x, uint64_t n, int32_t *__restrict__ out) {
+// deg[u] = forward neighbours (from the forward index) + backward neighbours (counted by nbr_keys_kernel)
+__global__ void __launch_bounds__(kThreads) pdegree_kernel(const uint32_t *__restrict__ fwd_start, uint32_t n_local, int32_t *__restrict__ deg,
+                                                           int32_t *__restrict__ max_deg) {
     int32_t m = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, x[i]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t d = deg[i] + (int32_t)(fwd_start[i + 1] - fwd_start[i]);
+        deg[i] = d;
+        m = max(m, d);
+    }
     m = warp_reduce_max(m);
-    if (lane_id() == 0 && m) atomicMax(out, m);
+    if (lane_id() == 0 && m) atomicMax(max_deg, m);
 }
-__global__ void pset_u64_kernel(uint64_t *p, uint64_t v) { *p = v; }
+
+__global__ void __launch_bounds__(kThreads) low_words_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)keys[i];
+}
 
 struct EvTimer {   // CUDA-event split timer on the context's stream
     kombgpu_ctx *ctx;
@@ -335,48 +329,46 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     KG_TRY(route_keys(c, swapped.p, n_fwd, g->step, true, &back, &n_back));
     swapped.release();
     g->st.ms_build_route += split.lap();
-    DevBuf<uint64_t> back_tmp;
-    uint64_t *back_sorted = back;
-    {
-        KG_ALLOC(ctx, back_tmp, n_back);
-        RadixPass passes[8];
-        const int np = plan_radix_passes(32, 32 + bits_for(g->step > 0 ? g->step - 1 : 0), 0, 0, passes);
-        KG_TRY(radix_sort_u64(ctx, back, back_tmp.p, n_back, passes, np, &back_sorted));
-    }
-    g->st.ms_build_sort += split.lap();
-
-    // 4. CSR of the local rows
-    DevBuf<uint32_t> fwd_start, back_start, d_err(ctx, 1);
-    DevBuf<uint64_t> row_ptr;
-    DevBuf<int32_t> deg, max_deg(ctx, 1);
-    DevBuf<uint32_t> col;
+    // 4. the local entries keyed by neighbour: (v << 32 | u - v_lo) for the forward edges, (w << 32 | u - v_lo) for what arrived;
+    //    degrees from the forward index plus a count of the arrivals; one sort on the neighbour bits
     const uint64_t n_dir = n_fwd + n_back;
+    if (n_dir >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "%llu adjacency entries on one rank exceed the 2^32 per-device limit", (unsigned long long)n_dir);
+    DevBuf<uint32_t> fwd_start, nbr_ptr, nbr, d_err(ctx, 1);
+    DevBuf<int32_t> deg, max_deg(ctx, 1);
+    DevBuf<uint64_t> keys_a, keys_b;
     KG_ALLOC(ctx, fwd_start, (size_t)n_local + 1);
-    KG_ALLOC(ctx, back_start, (size_t)n_local + 1);
-    KG_ALLOC(ctx, row_ptr, (size_t)n_local + 1);
     KG_ALLOC(ctx, deg, n_local);
-    KG_ALLOC(ctx, col, n_dir);
+    KG_ALLOC(ctx, keys_a, n_dir);
+    KG_ALLOC(ctx, keys_b, n_dir);
     if (!d_err || !max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
     KG_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
+    KG_CUDA(ctx, cudaMemsetAsync(deg.p, 0, (size_t)(n_local ? n_local : 1) * sizeof(int32_t), ctx->stream));
     KG_LAUNCH(ctx, row_bounds_checked_kernel, min(grid_for(n_fwd + 1, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, g->v_lo, n_local,
               n_global, fwd_start.p, d_err.p);
-    KG_LAUNCH(ctx, row_bounds_checked_kernel, min(grid_for(n_back + 1, kThreads), 148u * 16u), kThreads, 0, back_sorted, n_back, 0u, n_local,
-              n_global, back_start.p, d_err.p);
-    KG_TRY((device_scan<uint64_t>(ctx, n_local, PDegreeIn{fwd_start.p, back_start.p}, PDegreeOut{row_ptr.p, deg.p}, (uint64_t *)nullptr)));
-    KG_LAUNCH(ctx, pset_u64_kernel, 1, 1, 0, row_ptr.p + n_local, n_dir);
-    if (n_local) KG_LAUNCH(ctx, pmax_i32_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, deg.p, (uint64_t)n_local, max_deg.p);
-    if (n_fwd)
-        KG_LAUNCH(ctx, pfill_fwd_kernel, min(grid_for(n_fwd, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, g->v_lo, row_ptr.p,
-                  fwd_start.p, back_start.p, col.p);
-    if (n_back)
-        KG_LAUNCH(ctx, pfill_back_kernel, min(grid_for(n_back, kThreads), 148u * 16u), kThreads, 0, back_sorted, n_back, row_ptr.p,
-                  back_start.p, col.p);
+    if (n_dir)
+        KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
+                  n_global, keys_a.p, deg.p, d_err.p);
+    if (n_local)
+        KG_LAUNCH(ctx, pdegree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, fwd_start.p, n_local, deg.p, max_deg.p);
+    uint64_t *nsorted = keys_a.p;
+    {
+        RadixPass passes[8];
+        const int np = plan_radix_passes(32, 32 + bn, 0, 0, passes);
+        KG_TRY(radix_sort_u64(ctx, keys_a.p, keys_b.p, n_dir, passes, np, &nsorted));
+    }
+    g->st.ms_build_sort += split.lap();
+    KG_ALLOC(ctx, nbr_ptr, (size_t)n_global + 1);
+    KG_ALLOC(ctx, nbr, n_dir);
+    KG_LAUNCH(ctx, row_bounds_checked_kernel, min(grid_for(n_dir + 1, kThreads), 148u * 16u), kThreads, 0, nsorted, n_dir, 0u, n_global,
+              n_local ? n_local : 1u, nbr_ptr.p, d_err.p);
+    if (n_dir) KG_LAUNCH(ctx, low_words_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, nsorted, n_dir, nbr.p);
     uint32_t h_err = 0;
     int32_t h_max = 0;
     KG_TRY(read_back(ctx, d_err.p, &h_err, 1));
     KG_TRY(read_back(ctx, max_deg.p, &h_max, 1));
-    back_tmp.release();
+    keys_a.release();
+    keys_b.release();
     sym_release(c, mark);
     g->st.ms_build_csr = split.lap();
 
@@ -402,8 +394,8 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     g->edges = edges.take();
     g->mult = mult.take();
     g->fwd_start = fwd_start.take();
-    g->row_ptr = row_ptr.take();
-    g->col = col.take();
+    g->nbr_ptr = nbr_ptr.take();
+    g->nbr = nbr.take();
     g->deg = deg.take();
     g->st.ms_build = total.lap();
     return KOMBGPU_OK;
@@ -412,10 +404,10 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
 void dist_graph_release(kombgpu_dist_graph *g) {
     if (!g || !g->ctx) return;
     kombgpu_ctx *ctx = g->ctx;
-    void *ptrs[] = {g->edges, g->mult, g->fwd_start, g->row_ptr, g->col, g->deg, g->core, g->score};
+    void *ptrs[] = {g->edges, g->mult, g->fwd_start, g->nbr_ptr, g->nbr, g->deg, g->core, g->score};
     for (void *p : ptrs)
         if (p) ws_free(ctx, p);
-    g->edges = nullptr; g->mult = nullptr; g->fwd_start = nullptr; g->row_ptr = nullptr; g->col = nullptr;
+    g->edges = nullptr; g->mult = nullptr; g->fwd_start = nullptr; g->nbr_ptr = nullptr; g->nbr = nullptr;
     g->deg = nullptr; g->core = nullptr; g->score = nullptr;
 }
 

@@ -139,8 +139,8 @@ int kombgpu_dist_graph_device_arrays(const kombgpu_dist_graph *g, const uint64_t
                                      const uint64_t **edges_packed, const int32_t **degree, const int32_t **coreness,
                                      const double **score) {
     if (!g) return KOMBGPU_EINVAL;
-    if (row_ptr) *row_ptr = g->row_ptr;
-    if (col) *col = g->col;
+    if (row_ptr) *row_ptr = nullptr;   // the partitioned path keeps its adjacency grouped by neighbour (dgraph.cuh), not as rows
+    if (col) *col = nullptr;
     if (edges_packed) *edges_packed = g->edges;
     if (degree) *degree = g->deg;
     if (coreness) *coreness = g->has_core ? g->core : nullptr;

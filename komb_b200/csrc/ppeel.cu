@@ -5,25 +5,27 @@
 // function of the graph, so it is bit-exact whatever the partition.
 //
 // One persistent kernel per GPU.  Every rank owns the working degrees of its own unitigs and nobody else touches
-// them: a decrement of a unitig another rank owns travels as a MESSAGE -- its 32-bit id, stored straight into
-// that rank's mailbox (peer memory over NVLink; one mailbox per ordered pair of ranks, sized by the number of
-// CSR entries that cross that way, so it can never overflow and is never reused).  The peel advances in
-// SUB-ROUNDS, one per cascade generation:
+// them.  What travels between the GPUs is the FRONTIER, not the decrements: when a rank peels unitigs it appends
+// their ids to its LOG, and the new part of the log is copied into every peer's copy of that log (peer memory over
+// NVLink; the log of a rank holds each of its unitigs at most once, so it has a fixed size and is never reused).
+// Every rank then walks, for each newly logged unitig x of ANY rank, the list of its own unitigs adjacent to x
+// (pbuild.cu keeps the local adjacency grouped by neighbour) and decrements them in place.  Per peeled unitig four
+// bytes cross a link, whatever its degree; no atomics on shared counters per edge, no per-edge messages.
 //
-//   [scan]     first sub-round of a level k: local unitigs with degree == k form the frontier, the alive list is
-//              compacted, the smallest surviving degree is noted (empty levels are skipped with it)
-//   process    walk the rows of the frontier: local neighbours are decremented in place (the decrement that takes
-//              a degree to k discovers that unitig for the next sub-round), remote neighbours become messages
-//   exchange   ONE meeting of all ranks: each publishes, in every peer's control words, how many messages it has
-//              sent there so far and how much it did this sub-round, tagged with the sub-round number, and waits
-//              for the same from every peer (flags in peer memory; no host, no collective library)
-//   apply      decrement the targets of the messages that arrived; discoveries join the next frontier
-//
-// A level ends when no rank discovered, sliced or sent anything in a sub-round.  Two things keep a sub-round
-// cheap when cascades are thin (hundreds of dependent generations of a few unitigs each, the usual shape of a
-// collapsing core): a rank whose share of the sub-round is small runs it SOLO, on CTA 0 alone, while its other
-// CTAs wait on a local word -- no grid-wide barrier on the critical path -- and rows longer than kSliceLen are
-// cut into slices that the whole grid shares in the next sub-round.
+// The peel advances in SUB-ROUNDS, one per cascade generation:
+//   [scan]     first sub-round of a level k: local unitigs with degree == k are logged, the alive list is compacted,
+//              the smallest surviving degree is noted (empty levels are skipped with it)
+//   publish    copy the new part of the own log to every peer
+//   exchange   ONE meeting of all ranks: each stores, in every peer's control words, the length of its log and its
+//              pending work, tagged with the sub-round number, and waits for the same from every peer (flags in peer
+//              memory; no host, no collective library)
+//   walk       for every newly logged unitig of every rank: decrement the local neighbours; a decrement that takes a
+//              degree to k logs that unitig (coreness k) for the next sub-round
+// A level ends when no rank logged anything and no slices are pending.  Two things keep a sub-round cheap when
+// cascades are thin (hundreds of dependent generations of a few unitigs each, the usual shape of a collapsing core):
+// a rank whose share of the sub-round is small runs it SOLO, on CTA 0 alone, while its other CTAs wait on a local
+// word -- no grid-wide barrier on the critical path -- and neighbour lists longer than kSliceLen are cut into slices
+// that the whole grid shares in the next sub-round.
 //
 // Ranks that share one device (tests) run inside ONE cooperative grid, a group of CTAs per rank: kernels of
 // different ranks must never wait for one another on the same GPU.
@@ -41,10 +43,11 @@ namespace {
 constexpr int kPThreads = 512;
 constexpr int kPWarps = kPThreads / 32;
 constexpr int kPU = 4;                       // independent edge chains per lane
-constexpr uint32_t kSliceLen = 2048;         // rows longer than this are cut into slices of this many edges
-constexpr uint32_t kSoloFront = 512;         // a sub-round with at most this many frontier unitigs ...
-constexpr unsigned long long kSoloEdges = 16384;   // ... and this many edges to walk runs on CTA 0 alone
-constexpr unsigned long long kSoloInbox = 8192;    // same for the messages to apply
+constexpr uint32_t kSliceLen = 2048;         // neighbour lists longer than this are cut into slices of this many entries
+constexpr uint32_t kSoloWalk = 256;          // a sub-round with at most this many unitigs to walk ...
+constexpr unsigned long long kSoloEdges = 8192;    // ... and this many entries to visit runs on CTA 0 alone
+constexpr uint32_t kSoloCopy = 4096;         // a publish of at most this many ids is done by CTA 0 alone
+constexpr uint32_t kStage = 2048;            // discoveries a CTA collects in shared memory before one append to the log
 constexpr int kScanItems = 4;
 constexpr unsigned long long kPeelWatchdogNs = 20ull * 1000000000ull;
 constexpr unsigned long long kTagShift = 40, kValMask = (1ull << 40) - 1;
@@ -54,58 +57,57 @@ constexpr unsigned long long kTagShift = 40, kValMask = (1ull << 40) - 1;
 constexpr int kPlanRing = 256;
 constexpr uint32_t kPlanSync = 64;
 
-enum : uint32_t { kModeFull = 1, kModeSolo = 2, kFlagLevelOver = 4, kFlagDone = 8 };
+enum : uint32_t { kCopyFull = 1, kWalkFull = 2, kFlagLevelOver = 4, kFlagDone = 8 };
 
 // control words, one block per rank in symmetric memory: w[src][i] is written by rank src
-//   0: messages src has sent here so far   1: work src did this sub-round (discoveries + slices + messages)
-//   2: smallest surviving degree at src    3: frontier size at src
+//   0: length of src's log   1: slices pending at src   2: smallest surviving degree at src
 struct PeelCtl {
     unsigned long long w[kMaxRanks][4];
 };
 
 struct PRankState {
     unsigned long long bar_count, bar_gen;      // barrier of this rank's CTAs
-    unsigned long long plan_a[kPlanRing], plan_b[kPlanRing];   // leader -> CTAs: (sub-round << 8) | mode / flags, slot = sub-round % ring
+    unsigned long long plan_a[kPlanRing], plan_b[kPlanRing];   // leader -> CTAs: (sub-round << 8) | flags, slot = sub-round % ring
     int32_t k_next[kPlanRing];                  // level of the next sub-round when plan_b says the level is over
-    unsigned long long sent[kMaxRanks];         // messages sent to rank p so far
-    unsigned long long published[kMaxRanks];    // ... as of the last exchange
-    unsigned long long recv_hi[kMaxRanks];      // messages from rank q that have arrived
-    unsigned long long applied[kMaxRanks];      // ... and that have been applied
-    unsigned long long front_edges[2];          // sum of the row lengths of the frontier lists
-    unsigned long long work;                    // discoveries + slices + messages of the sub-round in progress
-    unsigned long long n_peeled;
-    unsigned long long msg_sent_total, msg_recv_total;
-    uint32_t front_cnt[2], slice_cnt[2];
+    unsigned long long log_hi[kMaxRanks];       // entries of rank q's log that have arrived here
+    unsigned long long log_lo[kMaxRanks];       // ... and that have been walked
+    unsigned long long n_visited;               // adjacency entries visited (statistics)
+    uint32_t log_cnt;                           // length of the own log (appended by scan and walk)
+    uint32_t published;                         // ... of which copied to the peers
+    uint32_t slice_cnt[2];
     uint32_t alive_out[2];                      // survivors written by a scan (slot = index of the list it wrote)
     int32_t local_min;
     int32_t max_core;
     uint32_t levels, subrounds, solo_subrounds;
-    uint32_t error;                             // 1 watchdog (CTAs), 2 watchdog (peers), 3 mailbox overflow, 4 bad message, 5 list overflow
+    uint32_t error;                             // 1 watchdog (CTAs), 2 watchdog (peers), 4 bad log entry, 5 list overflow
+    // where the leader thread's time goes (ns): 0 scan + barrier, 1 plan A, 2 publish copy (+ barrier), 3 wait for the
+    // peers, 4 exchange, 5 walk (+ barrier), 6 full publishes, 7 full walks
+    unsigned long long prof_ns[8];
+    uint32_t full_copy, full_walk;
 };
 
 struct PRank {
-    uint32_t n_local, v_lo, step;
+    uint32_t n_local, v_lo, n_global;
     int world, rank;
     uint32_t ctas;                              // CTAs that work for this rank
-    const uint64_t *row_ptr;
-    const uint32_t *col;
+    const uint32_t *nbr_ptr;                    // [n_global + 1]
+    const uint32_t *nbr;                        // local ids
     int32_t *deg;                               // working degrees (never clamped: only ever decremented)
     int32_t *core;
     uint32_t *alive[2];
-    uint32_t *front[2];
-    uint64_t *slices[2];                        // first_edge << 12 | length (length <= kSliceLen)
+    uint64_t *slices[2];                        // first_entry << 12 | (length - 1), length <= kSliceLen
     uint32_t slice_cap;
+    uint32_t log_cap;                           // entries per log (the largest n_local)
     PeelCtl *ctl_local;
     PeelCtl *ctl_peer[kMaxRanks];
-    const uint32_t *mbox_in[kMaxRanks];         // messages from rank q (local memory)
-    uint32_t *mbox_out[kMaxRanks];              // rank p's mailbox for this rank (peer memory)
-    unsigned long long mbox_out_cap[kMaxRanks];
+    uint32_t *log_local[kMaxRanks];             // this rank's copy of rank q's log (q == rank: the log itself)
+    uint32_t *log_peer[kMaxRanks];              // rank p's copy of THIS rank's log (peer memory)
     PRankState *st;
 };
 
-__device__ __forceinline__ unsigned long long ld_acq_sys(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long ld_acq_gpu(const unsigned long long *p) {
@@ -125,12 +127,12 @@ __device__ __forceinline__ unsigned long long pglobal_ns() {
     return t;
 }
 
-// barrier of one rank's CTAs; the fence is system-wide because messages stored into peer memory before it must be
-// visible at the peer before the leader publishes this rank's counts after it
-__device__ __forceinline__ void rank_barrier(PRankState *st, uint32_t ctas, unsigned long long &gen) {
+// barrier of one rank's CTAs.  sys_fence: the CTAs stored into peer memory before it, and those stores must be
+// visible at the peer before the leader publishes this rank's counts after it.
+__device__ __forceinline__ void rank_barrier(PRankState *st, uint32_t ctas, unsigned long long &gen, bool sys_fence) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (sys_fence) __threadfence_system(); else __threadfence();
         ++gen;
         const unsigned long long arrived = atomicAdd(&st->bar_count, 1ull) + 1ull;
         if (arrived == gen * ctas) {
@@ -160,7 +162,7 @@ __device__ __forceinline__ uint32_t wait_plan(unsigned long long *word, uint32_t
             if ((uint32_t)(w >> 8) == t) { res = (uint32_t)(w & 0xffu); break; }
             if ((++spins & 4095u) == 0 && (*(volatile uint32_t *)&st->error || pglobal_ns() - t0 > kPeelWatchdogNs)) {
                 atomicCAS(&st->error, 0u, 1u);
-                res = kFlagDone | kModeSolo;
+                res = kFlagDone;
                 break;
             }
         }
@@ -172,178 +174,183 @@ __device__ __forceinline__ uint32_t wait_plan(unsigned long long *word, uint32_t
     return r;
 }
 
-// a newly discovered unitig (its degree just reached k): coreness k, member of the next frontier
-// (count_work: discoveries of the process stage keep the level open; those of the apply stage are implied by the
-// messages that caused them, which were counted by their sender)
-__device__ __forceinline__ void discover(const PRank &R, PRankState *st, bool found, uint32_t loc, int32_t k, uint32_t nxt,
-                                         bool count_work) {
+// discoveries of a CTA are collected in shared memory and appended to the rank's log with ONE atomic per flush
+struct Stage {
+    uint32_t n;
+    uint32_t base;
+    uint32_t ids[kStage];
+    unsigned long long src_lo[kMaxRanks], src_cnt[kMaxRanks];   // walk stage: the fresh part of every rank's log
+};
+
+__device__ __forceinline__ void stage_flush(const PRank &R, PRankState *st, Stage &sg) {   // all threads of the CTA
+    __syncthreads();
+    const uint32_t n = min(sg.n, kStage);
+    __syncthreads();   // everyone has read the count before a fast warp's next batch can add to it
+    if (n) {
+        if (threadIdx.x == 0) sg.base = atomicAdd(&st->log_cnt, n);
+        __syncthreads();
+        const uint32_t base = sg.base;
+        uint32_t *log = R.log_local[R.rank];
+        for (uint32_t i = threadIdx.x; i < n; i += kPThreads) {
+            if (base + i < R.log_cap) log[base + i] = sg.ids[i];
+            else atomicCAS(&st->error, 0u, 5u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sg.n = 0;
+        __syncthreads();
+    }
+}
+
+// found lanes: coreness k, logged (global id).  Warp-aggregated append to the CTA's stage; when the stage is full the
+// excess goes straight to the log (rare: a flush follows every batch).
+__device__ __forceinline__ void discover(const PRank &R, PRankState *st, Stage &sg, uint32_t found_mask, bool found, uint32_t loc, int32_t k) {
+    if (found_mask == 0) return;
     const uint32_t lane = lane_id();
-    const uint32_t fm = __ballot_sync(kFullMask, found);
-    if (fm == 0) return;
-    uint32_t len = 0;
+    const uint32_t cnt = (uint32_t)__popc(found_mask);
+    uint32_t pos = 0;
+    if (lane == 0) pos = atomicAdd(&sg.n, cnt);
+    pos = __shfl_sync(kFullMask, pos, 0) + __popc(found_mask & lanemask_lt());
     if (found) {
         R.core[loc] = k;
-        len = (uint32_t)(R.row_ptr[loc + 1] - R.row_ptr[loc]);
-    }
-    const uint32_t tot_len = warp_reduce_add(len);
-    uint32_t pos = 0;
-    if (lane == 0) {
-        pos = atomicAdd(&st->front_cnt[nxt], (uint32_t)__popc(fm));
-        atomicAdd(&st->front_edges[nxt], (unsigned long long)tot_len);
-        if (count_work) atomicAdd(&st->work, (unsigned long long)__popc(fm));
-    }
-    pos = __shfl_sync(kFullMask, pos, 0) + __popc(fm & lanemask_lt());
-    if (found) {
-        if (pos < R.n_local) R.front[nxt][pos] = loc;
-        else atomicCAS(&st->error, 0u, 5u);
-    }
-}
-
-// one neighbour per lane: decrement it here, or send the decrement to its owner
-__device__ __forceinline__ void visit(const PRank &R, PRankState *st, bool valid, uint32_t u, int32_t k, uint32_t nxt, bool look_first) {
-    const uint32_t lane = lane_id();
-    const uint32_t owner = valid ? min(u / R.step, (uint32_t)R.world - 1u) : 0xffffffffu;
-    const bool local = valid && owner == (uint32_t)R.rank;
-    const bool remote = valid && !local;
-    // ---- remote: one message per neighbour, a warp's messages to one rank are stored as one run
-    if (__ballot_sync(kFullMask, remote)) {
-        const uint32_t same = __match_any_sync(kFullMask, remote ? owner : 0xffffffffu);
-        const uint32_t lead = (uint32_t)__ffs(same) - 1u;
-        unsigned long long base = 0;
-        if (remote && lane == lead) base = atomicAdd(&st->sent[owner], (unsigned long long)__popc(same));
-        base = __shfl_sync(kFullMask, base, lead);
-        if (remote) {
-            const unsigned long long pos = base + (unsigned long long)__popc(same & lanemask_lt());
-            if (pos < R.mbox_out_cap[owner]) R.mbox_out[owner][pos] = u;
-            else atomicCAS(&st->error, 0u, 3u);
+        if (pos < kStage) {
+            sg.ids[pos] = R.v_lo + loc;
+        } else {
+            const uint32_t at = atomicAdd(&st->log_cnt, 1u);
+            if (at < R.log_cap) R.log_local[R.rank][at] = R.v_lo + loc;
+            else atomicCAS(&st->error, 0u, 5u);
         }
     }
-    // ---- local
-    bool found = false;
-    const uint32_t loc = u - R.v_lo;
-    if (local) {
-        int32_t d = look_first ? __ldcg(&R.deg[loc]) : INT32_MAX;
-        if (d > k) d = atomicSub(&R.deg[loc], 1);
-        found = d == k + 1;
-    }
-    discover(R, st, found, loc, k, nxt, true);
 }
 
-// walk edges [0, total) of a batch of rows, one row per lane (row_begin, excl prefix of the lengths); all lanes call it
-__device__ __forceinline__ void walk_rows(const PRank &R, PRankState *st, uint64_t row_begin, uint32_t excl, uint32_t total, int32_t k,
-                                          uint32_t nxt) {
+// walk entries [0, total) of a batch of neighbour lists, one list per lane (first entry, excl prefix of the lengths)
+__device__ __forceinline__ void walk_lists(const PRank &R, PRankState *st, Stage &sg, uint32_t first, uint32_t excl, uint32_t total,
+                                           int32_t k) {
     const uint32_t lane = lane_id();
-    const uint32_t row_lo = (uint32_t)row_begin, row_hi = (uint32_t)(row_begin >> 32);
     const bool look_first = total > 32u * kPU;
     for (uint32_t base = 0; base < total; base += 32u * kPU) {
         uint32_t u[kPU];
-        bool valid[kPU];
+        int32_t d[kPU];
 #pragma unroll
         for (int t = 0; t < kPU; ++t) {
             const uint32_t e = base + t * 32u + lane;
-            valid[t] = false;
-            u[t] = 0;
+            u[t] = 0xffffffffu;
             if (base + t * 32u >= total) continue;   // warp-uniform
-            uint32_t j = 0;   // owner row: the last lane j with excl[j] <= e
+            uint32_t j = 0;   // owner list: the last lane j with excl[j] <= e
 #pragma unroll
             for (uint32_t s = 16; s > 0; s >>= 1) {
                 const uint32_t x = __shfl_sync(kFullMask, excl, (j + s) & 31u);
                 if (j + s < 32u && x <= e) j += s;
             }
             const uint32_t ex_j = __shfl_sync(kFullMask, excl, j);
-            const uint32_t lo = __shfl_sync(kFullMask, row_lo, j), hi = __shfl_sync(kFullMask, row_hi, j);
-            if (e < total) { u[t] = R.col[(((uint64_t)hi << 32) | lo) + (e - ex_j)]; valid[t] = true; }
+            const uint32_t f_j = __shfl_sync(kFullMask, first, j);
+            if (e < total) u[t] = R.nbr[f_j + (e - ex_j)];
         }
+        // degrees never go up and are never clamped: the decrement that takes a degree from k + 1 to k owns the unitig.
+        // Thin batches decrement without looking (one round trip less on a cascade's critical path); wide ones look first
+        // (no atomic on unitigs that are already gone).
+#pragma unroll
+        for (int t = 0; t < kPU; ++t)
+            d[t] = u[t] == 0xffffffffu ? INT32_MIN : (look_first ? __ldcg(&R.deg[u[t]]) : INT32_MAX);
+#pragma unroll
+        for (int t = 0; t < kPU; ++t) d[t] = d[t] > k ? atomicSub(&R.deg[u[t]], 1) : INT32_MIN;
 #pragma unroll
         for (int t = 0; t < kPU; ++t) {
             if (base + t * 32u >= total) continue;
-            visit(R, st, valid[t], u[t], k, nxt, look_first);
+            const bool found = d[t] == k + 1;
+            discover(R, st, sg, __ballot_sync(kFullMask, found), found, u[t], k);
         }
     }
 }
 
-// PROCESS stage for the warps [w0, w0 + nw) of this rank (global warp index gw): slices first, then the frontier
-__device__ __forceinline__ void process_stage(const PRank &R, PRankState *st, uint32_t gw, uint32_t nw, uint32_t cur, int32_t k) {
-    const uint32_t lane = lane_id();
+// WALK stage for the warps of one CTA (gw: index of this warp among the nw warps that walk for the rank): pending
+// slices, then the newly logged unitigs of every rank.  The CTA flushes its stage after every batch.
+__device__ __forceinline__ void walk_stage(const PRank &R, PRankState *st, Stage &sg, uint32_t gw, uint32_t nw, uint32_t cur, int32_t k) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t nxt = cur ^ 1u;
+    unsigned long long visited = 0;
+    // ---- slices (each is one batch of a warp)
     const uint32_t n_sl = __ldcg(&st->slice_cnt[cur]);
-    for (uint32_t i = gw; i < n_sl; i += nw) {
-        const uint64_t sl = __ldcg(&R.slices[cur][i]);
-        const uint64_t first = sl >> 12;
-        const uint32_t len = (uint32_t)(sl & 0xfffu) + 1u;
-        walk_rows(R, st, first, lane == 0 ? 0u : len, len, k, nxt);
-    }
-    const uint32_t n_f = __ldcg(&st->front_cnt[cur]);
-    uint32_t peeled = 0;
-    for (uint32_t c = gw; (uint64_t)c * 32u < n_f; c += nw) {
-        const uint32_t i = c * 32u + lane;
-        uint64_t row = 0;
-        uint32_t len = 0;
-        if (i < n_f) {
-            const uint32_t v = __ldcg(&R.front[cur][i]);
-            row = R.row_ptr[v];
-            len = (uint32_t)(R.row_ptr[v + 1] - row);
-            ++peeled;
+    const uint32_t cta_w0 = gw - warp, per_round = nw;   // the warps of a CTA advance together, one batch each per round
+    for (uint32_t i0 = cta_w0; i0 < n_sl; i0 += per_round) {
+        const uint32_t i = i0 + warp;
+        if (i < n_sl) {
+            const uint64_t sl = __ldcg(&R.slices[cur][i]);
+            const uint32_t len = (uint32_t)(sl & 0xfffu) + 1u;
+            walk_lists(R, st, sg, (uint32_t)(sl >> 12), lane == 0 ? 0u : len, len, k);
+            visited += lane == 0 ? len : 0u;
         }
-        // long rows are cut into slices that the whole grid walks in the next sub-round
+        stage_flush(R, st, sg);
+    }
+    // ---- newly logged unitigs, all sources concatenated
+    if (threadIdx.x < kMaxRanks) {
+        unsigned long long lo = 0, cnt = 0;
+        if ((int)threadIdx.x < R.world) {
+            lo = __ldcg(&st->log_lo[threadIdx.x]);
+            cnt = __ldcg(&st->log_hi[threadIdx.x]) - lo;
+        }
+        sg.src_lo[threadIdx.x] = lo;
+        sg.src_cnt[threadIdx.x] = cnt;
+    }
+    __syncthreads();
+    unsigned long long total_new = 0;
+    for (int q = 0; q < R.world; ++q) total_new += sg.src_cnt[q];
+    for (unsigned long long c0 = (unsigned long long)cta_w0 * 32ull; c0 < total_new; c0 += (unsigned long long)per_round * 32ull) {
+        const unsigned long long i = c0 + (unsigned long long)warp * 32ull + lane;
+        uint32_t first = 0, len = 0;
+        if (i < total_new) {
+            unsigned long long off = i;
+            int q = 0;
+            while (off >= sg.src_cnt[q]) { off -= sg.src_cnt[q]; ++q; }   // which source's log (i < total_new: q stays < world)
+            const uint32_t x = __ldcg(&R.log_local[q][sg.src_lo[q] + off]);
+            if (x >= R.n_global) {
+                atomicCAS(&st->error, 0u, 4u);
+            } else {
+                first = R.nbr_ptr[x];
+                len = R.nbr_ptr[x + 1] - first;
+            }
+        }
+        // long lists are cut into slices that the whole grid walks in the next sub-round
         const uint32_t n_cut = len > kSliceLen ? (len + kSliceLen - 1) / kSliceLen : 0u;
         if (__ballot_sync(kFullMask, n_cut != 0)) {
             const uint32_t inc = warp_incl_scan_add(n_cut);
             const uint32_t tot = __shfl_sync(kFullMask, inc, 31);
             uint32_t pos = 0;
-            if (lane == 0) {
-                pos = atomicAdd(&st->slice_cnt[nxt], tot);
-                atomicAdd(&st->work, (unsigned long long)tot);
-            }
+            if (lane == 0) pos = atomicAdd(&st->slice_cnt[nxt], tot);
             pos = __shfl_sync(kFullMask, pos, 0) + (inc - n_cut);
             for (uint32_t s = 0; s < n_cut; ++s) {
                 const uint32_t l = min(kSliceLen, len - s * kSliceLen);
-                if (pos + s < R.slice_cap) R.slices[nxt][pos + s] = ((row + (uint64_t)s * kSliceLen) << 12) | (uint64_t)(l - 1u);
+                if (pos + s < R.slice_cap) R.slices[nxt][pos + s] = ((uint64_t)(first + s * kSliceLen) << 12) | (uint64_t)(l - 1u);
                 else atomicCAS(&st->error, 0u, 5u);
             }
             if (n_cut) len = 0;
         }
         const uint32_t incl = warp_incl_scan_add(len);
-        walk_rows(R, st, row, incl - len, __shfl_sync(kFullMask, incl, 31), k, nxt);
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        walk_lists(R, st, sg, first, incl - len, total, k);
+        visited += lane == 0 ? total : 0u;
+        stage_flush(R, st, sg);
     }
-    peeled = warp_reduce_add(peeled);
-    if (lane == 0 && peeled) atomicAdd(&st->n_peeled, (unsigned long long)peeled);
+    if (lane == 0 && visited) atomicAdd(&st->n_visited, visited);
 }
 
-// APPLY stage: the messages that arrived since the last sub-round, spread over the warps [.., nw) of this rank
-__device__ __forceinline__ void apply_stage(const PRank &R, PRankState *st, uint32_t gw, uint32_t nw, uint32_t cur, int32_t k) {
-    const uint32_t lane = lane_id();
-    const uint32_t nxt = cur ^ 1u;
-    for (int q = 0; q < R.world; ++q) {
-        const unsigned long long lo = __ldcg(&st->applied[q]), hi = __ldcg(&st->recv_hi[q]);
-        for (unsigned long long base = lo + (unsigned long long)gw * 32ull; base < hi; base += (unsigned long long)nw * 32ull) {
-            const unsigned long long i = base + lane;
-            bool found = false;
-            uint32_t loc = 0;
-            if (i < hi) {
-                loc = __ldcg(&R.mbox_in[q][i]) - R.v_lo;
-                if (loc >= R.n_local) {
-                    atomicCAS(&st->error, 0u, 4u);
-                } else {
-                    int32_t d = __ldcg(&R.deg[loc]);
-                    if (d > k) d = atomicSub(&R.deg[loc], 1);
-                    found = d == k + 1;
-                }
-            }
-            discover(R, st, found, loc, k, nxt, false);
-        }
+// PUBLISH: copy the new part of the own log into every peer's copy (thread gthread of nthreads)
+__device__ __forceinline__ void publish_stage(const PRank &R, PRankState *st, uint32_t gthread, uint32_t nthreads) {
+    const uint32_t lo = __ldcg(&st->published), hi = __ldcg(&st->log_cnt);
+    const uint32_t *src = R.log_local[R.rank];
+    for (int p = 0; p < R.world; ++p) {
+        if (p == R.rank) continue;
+        uint32_t *dst = R.log_peer[p];
+        for (uint32_t i = lo + gthread; i < hi; i += nthreads) dst[i] = __ldcg(&src[i]);
     }
 }
 
-// SCAN stage of level k (all CTAs of the rank): frontier = alive unitigs at degree k, survivors compacted
+// SCAN stage of level k (all CTAs of the rank): alive unitigs at degree k are logged, survivors compacted
 __device__ __forceinline__ void scan_stage(const PRank &R, PRankState *st, uint32_t cta, const uint32_t *alive_src, uint32_t n_alive,
-                                           uint32_t *alive_dst, uint32_t *alive_out, uint32_t cur, int32_t k, uint32_t *s_scan,
-                                           uint32_t *s_base) {
+                                           uint32_t *alive_dst, uint32_t *alive_out, int32_t k, uint32_t *s_scan, uint32_t *s_base) {
     const uint32_t tid = threadIdx.x;
     int32_t local_min = INT32_MAX;
-    unsigned long long edges = 0;
-    uint32_t zero_deg = 0;
     const uint32_t tile = kPThreads * kScanItems;
+    uint32_t *log = R.log_local[R.rank];
     for (uint64_t t0 = (uint64_t)cta * tile; t0 < n_alive; t0 += (uint64_t)R.ctas * tile) {
         uint32_t v[kScanItems], flag[kScanItems];
         uint32_t mine = 0;
@@ -357,8 +364,7 @@ __device__ __forceinline__ void scan_stage(const PRank &R, PRankState *st, uint3
                 const int32_t d = __ldcg(&R.deg[v[j]]);
                 if (d == k) {
                     R.core[v[j]] = k;
-                    if (k > 0) { flag[j] = 1u; edges += (unsigned long long)(R.row_ptr[v[j] + 1] - R.row_ptr[v[j]]); }
-                    else ++zero_deg;   // no row to walk
+                    flag[j] = 1u;    // logged even at k = 0 (nothing to walk, but the log's length counts the peeled unitigs)
                 } else if (d > k) {
                     flag[j] = 0x10000u;
                     local_min = min(local_min, d);
@@ -370,135 +376,141 @@ __device__ __forceinline__ void scan_stage(const PRank &R, PRankState *st, uint3
         const uint32_t ex = block_excl_scan_add<uint32_t, kPThreads>(mine, s_scan, &total);
         if (tid == 0) {
             const uint32_t nf = total & 0xffffu, ns = total >> 16;
-            s_base[0] = nf ? atomicAdd(&st->front_cnt[cur], nf) : 0;
+            s_base[0] = nf ? atomicAdd(&st->log_cnt, nf) : 0;
             s_base[1] = ns ? atomicAdd(alive_out, ns) : 0;
         }
         __syncthreads();
         uint32_t fpos = s_base[0] + (ex & 0xffffu), spos = s_base[1] + (ex >> 16);
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j) {
-            if (flag[j] == 1u) R.front[cur][fpos++] = v[j];
-            else if (flag[j]) alive_dst[spos++] = v[j];
+            if (flag[j] == 1u) {
+                if (fpos < R.log_cap) log[fpos] = R.v_lo + v[j];
+                else atomicCAS(&st->error, 0u, 5u);
+                ++fpos;
+            } else if (flag[j]) {
+                alive_dst[spos++] = v[j];
+            }
         }
         __syncthreads();
     }
     local_min = warp_reduce_min(local_min);
-    zero_deg = warp_reduce_add(zero_deg);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) edges += __shfl_xor_sync(kFullMask, edges, o);
-    if (lane_id() == 0) {
-        if (local_min != INT32_MAX) atomicMin(&st->local_min, local_min);
-        if (edges) atomicAdd(&st->front_edges[cur], edges);
-        if (zero_deg) atomicAdd(&st->n_peeled, (unsigned long long)zero_deg);
-    }
+    if (lane_id() == 0 && local_min != INT32_MAX) atomicMin(&st->local_min, local_min);
 }
 
-// The leader (warp 0 of the rank's CTA 0) meets the other ranks: publish, wait, decide.
-__device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, uint32_t t, uint32_t cur, int32_t k, bool scanned,
-                                                uint32_t front_now) {
+// The leader (warp 0 of the rank's CTA 0) meets the other ranks: publish the counts, wait, decide.
+__device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, uint32_t t, uint32_t cur, int32_t k, bool scanned) {
     const uint32_t lane = lane_id();
     const int world = R.world;
     const unsigned long long tag = (unsigned long long)t << kTagShift;
-    unsigned long long work = 0, sent_before = 0;
+    unsigned long long log_len = 0, n_slices = 0;
     int32_t lmin = INT32_MAX;
     if (lane == 0) {
-        work = __ldcg(&st->work);
+        log_len = __ldcg(&st->log_cnt);
+        n_slices = __ldcg(&st->slice_cnt[cur]);
         lmin = __ldcg(&st->local_min);
+        st->published = (uint32_t)log_len;
     }
-    work = __shfl_sync(kFullMask, work, 0);
+    log_len = __shfl_sync(kFullMask, log_len, 0);
+    n_slices = __shfl_sync(kFullMask, n_slices, 0);
     lmin = __shfl_sync(kFullMask, lmin, 0);
-    // messages sent this sub-round count as work: a level is over only when nothing was discovered, sliced or sent
-    unsigned long long sent_q = 0;
-    if ((int)lane < world) {
-        sent_q = __ldcg(&st->sent[lane]);
-        sent_before = st->published[lane];
-        st->published[lane] = sent_q;
-    }
-    unsigned long long sent_now = (int)lane < world ? sent_q - sent_before : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sent_now += __shfl_xor_sync(kFullMask, sent_now, o);
-    work += sent_now;
-    if (work > kValMask) work = kValMask;
-    __threadfence_system();
+    __threadfence_system();   // the copies of the log this rank made are visible at the peers before the counts
     if ((int)lane < world) {
         PeelCtl *dst = R.ctl_peer[lane];
-        st_relaxed_sys(&dst->w[R.rank][1], tag | work);
+        st_relaxed_sys(&dst->w[R.rank][1], tag | n_slices);
         st_relaxed_sys(&dst->w[R.rank][2], tag | (unsigned long long)(uint32_t)lmin);
-        st_relaxed_sys(&dst->w[R.rank][3], tag | (unsigned long long)front_now);
-        st_relaxed_sys(&dst->w[R.rank][0], tag | sent_q);
+        st_relaxed_sys(&dst->w[R.rank][0], tag | log_len);
     }
     // wait for every rank's words of this sub-round
-    unsigned long long w0 = 0, w1 = 0, w2 = (unsigned long long)(uint32_t)INT32_MAX, w3 = 0;
+    const unsigned long long t_wait = pglobal_ns();
+    unsigned long long w0 = 0, w1 = 0, w2 = (unsigned long long)(uint32_t)INT32_MAX;
     bool failed = false;
     if ((int)lane < world) {
         const PeelCtl *mine = R.ctl_local;
-        const unsigned long long t0 = pglobal_ns();
         uint32_t spins = 0;
         while (true) {
-            w0 = ld_acq_sys(&mine->w[lane][0]);
-            w1 = ld_acq_sys(&mine->w[lane][1]);
-            w2 = ld_acq_sys(&mine->w[lane][2]);
-            w3 = ld_acq_sys(&mine->w[lane][3]);
-            if ((w0 >> kTagShift) == t && (w1 >> kTagShift) == t && (w2 >> kTagShift) == t && (w3 >> kTagShift) == t) break;
-            if ((++spins & 1023u) == 0 && (*(volatile uint32_t *)&st->error || pglobal_ns() - t0 > kPeelWatchdogNs)) { failed = true; break; }
+            w0 = ld_relaxed_sys(&mine->w[lane][0]);
+            w1 = ld_relaxed_sys(&mine->w[lane][1]);
+            w2 = ld_relaxed_sys(&mine->w[lane][2]);
+            if ((w0 >> kTagShift) == t && (w1 >> kTagShift) == t && (w2 >> kTagShift) == t) break;
+            if ((++spins & 1023u) == 0 && (*(volatile uint32_t *)&st->error || pglobal_ns() - t_wait > kPeelWatchdogNs)) { failed = true; break; }
         }
-        w0 &= kValMask; w1 &= kValMask; w2 &= kValMask; w3 &= kValMask;
+        w0 &= kValMask; w1 &= kValMask; w2 &= kValMask;
     }
+    __threadfence_system();   // acquire: the peers' log entries are read after their counts
+    if (lane == 0) st->prof_ns[3] += pglobal_ns() - t_wait;
     if (__ballot_sync(kFullMask, failed)) {
         if (lane == 0) {
             atomicCAS(&st->error, 0u, 2u);
-            st_rel_gpu(&st->plan_b[t % kPlanRing], ((unsigned long long)t << 8) | kFlagDone | kModeSolo);
+            st_rel_gpu(&st->plan_b[t % kPlanRing], ((unsigned long long)t << 8) | kFlagDone);
         }
         return;
     }
-    unsigned long long inbox = 0;
+    unsigned long long fresh = 0;
     if ((int)lane < world) {
-        const unsigned long long before = __ldcg(&st->recv_hi[lane]);
-        st->applied[lane] = before;
-        st->recv_hi[lane] = w0;
-        inbox = w0 - before;
+        const unsigned long long before = __ldcg(&st->log_hi[lane]);
+        st->log_lo[lane] = before;
+        st->log_hi[lane] = w0;
+        fresh = w0 - before;
     }
-    unsigned long long g_work = (int)lane < world ? w1 : 0ull, g_front = (int)lane < world ? w3 : 0ull, g_inbox = inbox;
+    unsigned long long g_fresh = fresh, g_slices = (int)lane < world ? w1 : 0ull, g_total = (int)lane < world ? w0 : 0ull;
     uint32_t g_min = (int)lane < world ? (uint32_t)w2 : (uint32_t)INT32_MAX;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        g_work += __shfl_xor_sync(kFullMask, g_work, o);
-        g_front += __shfl_xor_sync(kFullMask, g_front, o);
-        g_inbox += __shfl_xor_sync(kFullMask, g_inbox, o);
+        g_fresh += __shfl_xor_sync(kFullMask, g_fresh, o);
+        g_slices += __shfl_xor_sync(kFullMask, g_slices, o);
+        g_total += __shfl_xor_sync(kFullMask, g_total, o);
         g_min = min(g_min, __shfl_xor_sync(kFullMask, g_min, o));
     }
-    __threadfence();   // every lane's stores to applied / recv_hi are ordered before lane 0's release of the plan
+    __threadfence();   // every lane's stores to log_lo / log_hi are ordered before lane 0's release of the plan
     __syncwarp();
+    // how much is there to walk HERE: the fresh unitigs' local neighbour lists (exact when there are few of them)
+    unsigned long long my_entries = ~0ull;
+    if (g_fresh <= kSoloWalk && n_slices == 0) {
+        unsigned long long e = 0;
+        for (unsigned long long i = lane; i < g_fresh; i += 32) {
+            unsigned long long off = i;
+            int q = 0;
+            while (true) {
+                const unsigned long long cq = st->log_hi[q] - st->log_lo[q];
+                if (off < cq) break;
+                off -= cq;
+                ++q;
+            }
+            const uint32_t x = __ldcg(&R.log_local[q][st->log_lo[q] + off]);
+            if (x < R.n_global) e += R.nbr_ptr[x + 1] - R.nbr_ptr[x];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(kFullMask, e, o);
+        my_entries = e;
+    }
     if (lane == 0) {
-        uint32_t flags = g_inbox <= kSoloInbox ? kModeSolo : kModeFull;
-        st->msg_recv_total += g_inbox;
+        uint32_t flags = (my_entries <= kSoloEdges) ? 0u : kWalkFull;
         st->subrounds = t;
-        if (scanned && g_front) { st->levels += 1; st->max_core = k; }
-        if (g_work == 0) {
-            // nothing was discovered, sliced or sent anywhere: the level is over
+        if (scanned && g_fresh) { st->levels += 1; st->max_core = k; }
+        if (g_fresh == 0 && g_slices == 0) {
+            // nobody logged anything and nothing is pending: the level is over
             flags |= kFlagLevelOver;
-            if (scanned && g_front == 0) {
+            if (g_total >= R.n_global) flags |= kFlagDone;               // every unitig of the graph is in a log
+            if (scanned) {
                 if (g_min == (uint32_t)INT32_MAX) flags |= kFlagDone;    // nothing alive anywhere
                 st->k_next[t % kPlanRing] = (int32_t)g_min;               // the level was empty: skip to the smallest degree
             } else {
                 st->k_next[t % kPlanRing] = k + 1;
             }
             st->local_min = INT32_MAX;
+        } else if (!(flags & kWalkFull)) {
+            st->solo_subrounds += 1;
         }
-        // the list that was walked this sub-round becomes the one the next sub-round appends to
-        st->front_cnt[cur] = 0;
-        st->slice_cnt[cur] = 0;
-        st->front_edges[cur] = 0;
-        st->work = 0;
         __threadfence();
         st_rel_gpu(&st->plan_b[t % kPlanRing], ((unsigned long long)t << 8) | flags);
     }
 }
 
-__global__ void __launch_bounds__(kPThreads) ppeel_kernel(const PRank *ranks, uint32_t ctas_per_rank) {
+__global__ void __launch_bounds__(kPThreads, 2) ppeel_kernel(const PRank *ranks, uint32_t ctas_per_rank) {
     __shared__ uint32_t s_scan[kPWarps + 1];
     __shared__ uint32_t s_base[2];
     __shared__ uint32_t s_bcast;
+    __shared__ Stage s_stage;
     const PRank R = ranks[blockIdx.x / ctas_per_rank];
     PRankState *st = R.st;
     const uint32_t cta = blockIdx.x % ctas_per_rank;
@@ -508,62 +520,78 @@ __global__ void __launch_bounds__(kPThreads) ppeel_kernel(const PRank *ranks, ui
     uint32_t t = 1;          // sub-round number (tags of zero-initialised control words are 0)
     int32_t k = 0;
     bool scan = true;
-    uint32_t cur = 0;
+    uint32_t cur = 0;        // slice list walked this sub-round
     const uint32_t *alive_src = nullptr;   // nullptr: every local unitig
     uint32_t alive_i = 0;
     uint32_t n_alive = R.n_local;
+    if (tid == 0) s_stage.n = 0;
+    __syncthreads();
 
+    const bool prof = leader_cta && tid == 0;
+    unsigned long long tp = prof ? pglobal_ns() : 0ull;
+#define KG_PROF(slot)                                               \
+    if (prof) {                                                     \
+        const unsigned long long now_ = pglobal_ns();               \
+        st->prof_ns[slot] += now_ - tp;                             \
+        tp = now_;                                                  \
+    }
     while (true) {
         if (scan) {
-            scan_stage(R, st, cta, alive_src, n_alive, R.alive[alive_i], &st->alive_out[alive_i], cur, k, s_scan, s_base);
-            rank_barrier(st, R.ctas, bar_gen);
+            scan_stage(R, st, cta, alive_src, n_alive, R.alive[alive_i], &st->alive_out[alive_i], k, s_scan, s_base);
+            rank_barrier(st, R.ctas, bar_gen, false);
             n_alive = __ldcg(&st->alive_out[alive_i]);
             alive_src = R.alive[alive_i];
             alive_i ^= 1u;
             // the other slot was last read two scans ago (every CTA has passed a barrier since): re-arm it for the next scan
             if (leader_cta && tid == 0) st->alive_out[alive_i] = 0;
         } else if ((t % kPlanSync) == 0) {
-            rank_barrier(st, R.ctas, bar_gen);   // bounds the leader's lead over the other CTAs (plan ring)
+            rank_barrier(st, R.ctas, bar_gen, false);   // bounds the leader's lead over the other CTAs (plan ring)
         }
-        // ---- plan A: who walks the frontier
-        uint32_t front_now = 0;
+        KG_PROF(0);
+        // ---- plan A: who copies the new part of the log to the peers
         if (leader_cta && tid == 0) {
-            const uint32_t nf = __ldcg(&st->front_cnt[cur]), ns = __ldcg(&st->slice_cnt[cur]);
-            const unsigned long long ne = __ldcg(&st->front_edges[cur]);
-            const uint32_t mode = (ns == 0 && nf <= kSoloFront && ne <= kSoloEdges) ? kModeSolo : kModeFull;
-            if (mode == kModeSolo) st->solo_subrounds += 1;
-            s_base[0] = nf;
+            const uint32_t fresh = __ldcg(&st->log_cnt) - __ldcg(&st->published);
+            const uint32_t mode = (R.world > 1 && fresh > kSoloCopy) ? kCopyFull : 0u;
             __threadfence();
             st_rel_gpu(&st->plan_a[t % kPlanRing], ((unsigned long long)t << 8) | mode);
         }
         const uint32_t mode_a = wait_plan(&st->plan_a[t % kPlanRing], t, st, &s_bcast);
         if (mode_a & kFlagDone) break;   // watchdog
-        if (leader_cta) front_now = s_base[0];
-        // ---- process
-        if (mode_a & kModeFull) {
-            process_stage(R, st, cta * kPWarps + warp, R.ctas * kPWarps, cur, k);
-            rank_barrier(st, R.ctas, bar_gen);
+        KG_PROF(1);
+        // ---- publish
+        if (mode_a & kCopyFull) {
+            publish_stage(R, st, cta * kPThreads + tid, R.ctas * kPThreads);
+            rank_barrier(st, R.ctas, bar_gen, true);
+            if (prof) { st->full_copy += 1; st->prof_ns[6] += pglobal_ns() - tp; }
         } else if (leader_cta) {
-            process_stage(R, st, warp, kPWarps, cur, k);
+            if (R.world > 1) publish_stage(R, st, tid, kPThreads);
             __syncthreads();
             if (tid == 0) __threadfence_system();
             __syncthreads();
         }
+        KG_PROF(2);
         // ---- exchange
-        if (leader_cta && warp == 0) leader_exchange(R, st, t, cur, k, scan, front_now);
+        if (leader_cta && warp == 0) leader_exchange(R, st, t, cur, k, scan);
         const uint32_t flags = wait_plan(&st->plan_b[t % kPlanRing], t, st, &s_bcast);
-        // ---- apply
-        if (flags & kModeFull) {
-            apply_stage(R, st, cta * kPWarps + warp, R.ctas * kPWarps, cur, k);
-            rank_barrier(st, R.ctas, bar_gen);
-        } else if (leader_cta) {
-            apply_stage(R, st, warp, kPWarps, cur, k);
-            __syncthreads();
-            if (tid == 0) __threadfence();
-            __syncthreads();
+        KG_PROF(4);
+        // ---- walk
+        if (!(flags & kFlagLevelOver)) {
+            if (flags & kWalkFull) {
+                walk_stage(R, st, s_stage, cta * kPWarps + warp, R.ctas * kPWarps, cur, k);
+                rank_barrier(st, R.ctas, bar_gen, false);
+                if (prof) { st->full_walk += 1; st->prof_ns[7] += pglobal_ns() - tp; }
+            } else if (leader_cta) {
+                walk_stage(R, st, s_stage, warp, kPWarps, cur, k);
+                __syncthreads();
+                if (tid == 0) __threadfence();
+                __syncthreads();
+            }
+            // the slice list that was walked becomes the one the next sub-round's walk appends to
+            if (leader_cta && tid == 0) st->slice_cnt[cur] = 0;
+            cur ^= 1u;
         }
+        KG_PROF(5);
         if ((flags & kFlagDone) || *(volatile uint32_t *)&st->error) break;
-        cur ^= 1u;
         ++t;
         if (t >= (1u << 24) - 2u) { if (tid == 0) atomicCAS(&st->error, 0u, 1u); break; }
         if (flags & kFlagLevelOver) {
@@ -573,24 +601,7 @@ __global__ void __launch_bounds__(kPThreads) ppeel_kernel(const PRank *ranks, ui
             scan = false;
         }
     }
-}
-
-// owners of the CSR entries of the local rows: cross[p] = entries whose target rank p owns
-__global__ void __launch_bounds__(256) cross_count_kernel(const uint32_t *__restrict__ col, uint64_t n, uint32_t step, int world,
-                                                          unsigned long long *__restrict__ cross) {
-    __shared__ uint32_t s_cnt[kMaxRanks];
-    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t lane = lane_id();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
-        const uint64_t i = base + threadIdx.x;
-        const uint32_t o = i < n ? min(col[i] / step, (uint32_t)world - 1u) : 0xffffffffu;
-        const uint32_t same = __match_any_sync(kFullMask, o);
-        if (o != 0xffffffffu && lane == (uint32_t)__ffs(same) - 1u) atomicAdd(&s_cnt[o], (uint32_t)__popc(same));
-    }
-    __syncthreads();
-    if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&cross[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+#undef KG_PROF
 }
 
 }  // namespace
@@ -610,49 +621,29 @@ int dist_peel(kombgpu_dist_graph *g) {
     }
     KG_CUDA(ctx, cudaMemsetAsync(g->core, 0, (size_t)(n_local ? n_local : 1) * sizeof(int32_t), ctx->stream));
 
-    // mailbox sizes: cross[q][p] = CSR entries of rank q whose target rank p owns
-    DevBuf<unsigned long long> d_cross(ctx, kMaxRanks);
-    if (!d_cross) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
-    KG_CUDA(ctx, cudaMemsetAsync(d_cross.p, 0, kMaxRanks * sizeof(unsigned long long), ctx->stream));
-    if (g->n_directed)
-        KG_LAUNCH(ctx, cross_count_kernel, min(ceil_div_u64(g->n_directed, 256), (uint32_t)ctx->sm_count * 8u), 256, 0, g->col,
-                  g->n_directed, g->step, world, d_cross.p);
-    unsigned long long h_cross[kMaxRanks] = {}, matrix[kMaxRanks * kMaxRanks];
-    KG_TRY(read_back(ctx, d_cross.p, h_cross, kMaxRanks));
-    KG_TRY(comm_exchange(c, h_cross, world, matrix));   // matrix[q * world + p]
-    unsigned long long in_off[kMaxRanks + 1] = {}, out_off[kMaxRanks] = {}, max_in = 0;
-    for (int p = 0; p < world; ++p) {
-        unsigned long long tot = 0;
-        for (int q = 0; q < world; ++q) {
-            if (p == c->rank) in_off[q] = tot;
-            if (q == c->rank) out_off[p] = tot;    // where this rank's messages start in rank p's mailbox block
-            tot += (q == p) ? 0ull : matrix[q * world + p];
-        }
-        if (p == c->rank) in_off[world] = tot;
-        if (tot > max_in) max_in = tot;
-    }
+    // symmetric: one log per rank (every rank holds a copy of every rank's log) + the control words
+    const uint32_t log_cap = g->step;   // the largest n_local
     const SymMark mark = sym_mark(c);
-    uint32_t *mbox = nullptr;
-    PeerPtrs<uint32_t> mbox_peers{};
+    uint32_t *logs = nullptr;
+    PeerPtrs<uint32_t> logs_peers{};
     PeelCtl *ctl = nullptr;
     PeerPtrs<PeelCtl> ctl_peers{};
-    KG_TRY(sym_alloc(c, (size_t)max_in, &mbox, &mbox_peers));
+    KG_TRY(sym_alloc(c, (size_t)world * log_cap, &logs, &logs_peers));
     KG_TRY(sym_alloc(c, 1, &ctl, &ctl_peers));
     KG_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(PeelCtl), ctx->stream));
 
     // per-rank lists and state
     DevBuf<int32_t> work;
-    DevBuf<uint32_t> alive_a, alive_b, front_a, front_b;
+    DevBuf<uint32_t> alive_a, alive_b;
     DevBuf<uint64_t> slices_a, slices_b;
     DevBuf<PRankState> state(ctx, 1);
     DevBuf<PRank> desc(ctx, kMaxRanks);
-    const uint64_t slice_cap64 = g->n_directed / kSliceLen + (uint64_t)n_local + 64;
-    if (slice_cap64 >= 0xffffffffull || g->n_directed >= (1ull << 51)) return ctx_fail(ctx, KOMBGPU_EINVAL, "partition too large for the slice encoding");
+    // every unitig of the graph is walked once here, its list cut into ceil(len / kSliceLen) slices when it is long
+    const uint64_t slice_cap64 = g->n_directed / kSliceLen + (uint64_t)g->n_global / 64 + 1024;
+    if (slice_cap64 >= 0xffffffffull) return ctx_fail(ctx, KOMBGPU_EINVAL, "partition too large for the slice list");
     KG_ALLOC(ctx, work, n_local);
     KG_ALLOC(ctx, alive_a, n_local);
     KG_ALLOC(ctx, alive_b, n_local);
-    KG_ALLOC(ctx, front_a, n_local);
-    KG_ALLOC(ctx, front_b, n_local);
     KG_ALLOC(ctx, slices_a, slice_cap64);
     KG_ALLOC(ctx, slices_b, slice_cap64);
     if (!state || !desc) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
@@ -669,16 +660,16 @@ int dist_peel(kombgpu_dist_graph *g) {
     if (ctas_per_rank < 1) return ctx_fail(ctx, KOMBGPU_EINVAL, "too many ranks on one device");
 
     PRank R{};
-    R.n_local = n_local; R.v_lo = g->v_lo; R.step = g->step; R.world = world; R.rank = c->rank; R.ctas = ctas_per_rank;
-    R.row_ptr = g->row_ptr; R.col = g->col; R.deg = work.p; R.core = g->core;
-    R.alive[0] = alive_a.p; R.alive[1] = alive_b.p; R.front[0] = front_a.p; R.front[1] = front_b.p;
+    R.n_local = n_local; R.v_lo = g->v_lo; R.n_global = g->n_global; R.world = world; R.rank = c->rank; R.ctas = ctas_per_rank;
+    R.nbr_ptr = g->nbr_ptr; R.nbr = g->nbr; R.deg = work.p; R.core = g->core;
+    R.alive[0] = alive_a.p; R.alive[1] = alive_b.p;
     R.slices[0] = slices_a.p; R.slices[1] = slices_b.p; R.slice_cap = (uint32_t)slice_cap64;
+    R.log_cap = log_cap;
     R.ctl_local = ctl;
     for (int q = 0; q < world; ++q) {
         R.ctl_peer[q] = ctl_peers.p[q];
-        R.mbox_in[q] = mbox + in_off[q];
-        R.mbox_out[q] = mbox_peers.p[q] + out_off[q];
-        R.mbox_out_cap[q] = q == c->rank ? 0ull : matrix[c->rank * world + q];
+        R.log_local[q] = logs + (size_t)q * log_cap;                         // my copy of rank q's log
+        R.log_peer[q] = logs_peers.p[q] + (size_t)c->rank * log_cap;        // rank q's copy of my log
     }
     R.st = state.p;
 
@@ -721,25 +712,29 @@ int dist_peel(kombgpu_dist_graph *g) {
 
     PRankState fin{};
     KG_TRY(read_back(ctx, state.p, &fin, 1));
-    unsigned long long sent_total = 0;
-    for (int q = 0; q < world; ++q) sent_total += fin.sent[q];
-    // global figures; also: nobody releases its mailbox while a peer may still be writing
-    unsigned long long mine[4] = {fin.error, fin.n_peeled, (unsigned long long)(uint32_t)fin.max_core, sent_total}, all[kMaxRanks * 4];
-    KG_TRY(comm_exchange(c, mine, 4, all));
+    // global figures; also: nobody releases its logs while a peer may still be writing
+    unsigned long long mine[3] = {fin.error, fin.log_cnt, (unsigned long long)(uint32_t)fin.max_core}, all[kMaxRanks * 3];
+    KG_TRY(comm_exchange(c, mine, 3, all));
     sym_release(c, mark);
     uint64_t peeled = 0;
     for (int q = 0; q < world; ++q) {
-        if (all[q * 4]) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "partitioned peel: rank %d reports error %llu (1/2 watchdog, 3 mailbox, 4 bad message, 5 list)", q, all[q * 4]);
-        peeled += all[q * 4 + 1];
+        if (all[q * 3]) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "partitioned peel: rank %d reports error %llu (1/2 watchdog, 4 bad log entry, 5 list overflow)", q, all[q * 3]);
+        peeled += all[q * 3 + 1];
     }
     if (peeled != g->n_global) return ctx_fail(ctx, KOMBGPU_EINTERNAL, "partitioned peel ended with %llu of %u unitigs peeled", (unsigned long long)peeled, g->n_global);
     g->st.max_coreness = fin.max_core;
     g->st.peel_levels = fin.levels;
     g->st.peel_subrounds = fin.subrounds;
     g->st.peel_solo_subrounds = fin.solo_subrounds;
-    g->st.n_messages_sent = sent_total;
-    g->st.n_messages_recv = fin.msg_recv_total;
+    g->st.n_messages_sent = (uint64_t)fin.log_cnt * (uint64_t)(world - 1);   // ids copied to peers
+    g->st.n_messages_recv = peeled - fin.log_cnt;
     g->has_core = true;
+    if (getenv("KOMBGPU_DEBUG"))
+        fprintf(stderr, "[kombgpu] rank %d ppeel: levels %u subrounds %u (solo walks %u; full copies %u, full walks %u) ctas %u | leader ms: scan %.3f planA %.3f "
+                "publish %.3f (full %.3f) exchange %.3f (wait peers %.3f) walk %.3f (full %.3f) | peeled here %u, entries visited %llu\n",
+                c->rank, fin.levels, fin.subrounds, fin.solo_subrounds, fin.full_copy, fin.full_walk, ctas_per_rank, fin.prof_ns[0] * 1e-6,
+                fin.prof_ns[1] * 1e-6, fin.prof_ns[2] * 1e-6, fin.prof_ns[6] * 1e-6, fin.prof_ns[4] * 1e-6, fin.prof_ns[3] * 1e-6,
+                fin.prof_ns[5] * 1e-6, fin.prof_ns[7] * 1e-6, fin.log_cnt, fin.n_visited);
     KG_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
     KG_CUDA(ctx, cudaEventSynchronize(ev1));
     cudaEventElapsedTime(&g->st.ms_peel, ev0, ev1);

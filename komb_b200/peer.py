@@ -133,6 +133,8 @@ class DistGraph:
         out = out or {}
         r = {"degree": out.get("degree", np.empty(n, np.int32))[:n], "coreness": out.get("coreness", np.empty(n, np.int32))[:n],
              "score": out.get("score", np.empty(n, np.float64))[:n]}
+        if any(a.shape[0] != n for a in r.values()):
+            raise ValueError("out= buffers are too small for this rank's unitigs")
         self._ctx._check(self._lib.kombgpu_dist_graph_results(self._h, c_void_p(r["degree"].ctypes.data), c_void_p(r["coreness"].ctypes.data),
                                                               c_void_p(r["score"].ctypes.data)))
         r["v_lo"] = st["v_lo"]
@@ -153,6 +155,8 @@ class DistGraph:
         out = out or {}
         fp = out.get("fwd_ptr", np.empty(st["n_local"] + 1, np.uint64))[:st["n_local"] + 1]
         v = out.get("v", np.empty(st["n_fwd_local"], np.uint32))[:st["n_fwd_local"]]
+        if fp.shape[0] != st["n_local"] + 1 or v.shape[0] != st["n_fwd_local"]:
+            raise ValueError("out= buffers are too small for this rank's slice of the edge list")
         self._ctx._check(self._lib.kombgpu_dist_graph_edges_csr(self._h, c_void_p(fp.ctypes.data), c_void_p(v.ctypes.data)))
         return fp, v
 
