@@ -15,7 +15,8 @@
 // The peel advances in SUB-ROUNDS, one per cascade generation:
 //   [scan]     first sub-round of a level k: local unitigs with degree == k are logged, the alive list is compacted,
 //              the smallest surviving degree is noted (empty levels are skipped with it)
-//   publish    copy the new part of the own log to every peer
+//   publish    copy the new part of the own log to every peer (log slots are written once and valid when they differ
+//              from an EMPTY marker, so the copy needs no fence and no acknowledgement before it is announced)
 //   exchange   ONE meeting of all ranks: each stores, in every peer's control words, the length of its log and its
 //              pending work, tagged with the sub-round number, and waits for the same from every peer (flags in peer
 //              memory; no host, no collective library)
@@ -44,9 +45,9 @@ constexpr int kPThreads = 512;
 constexpr int kPWarps = kPThreads / 32;
 constexpr int kPU = 4;                       // independent edge chains per lane
 constexpr uint32_t kSliceLen = 2048;         // neighbour lists longer than this are cut into slices of this many entries
-constexpr uint32_t kSoloWalk = 256;          // a sub-round with at most this many unitigs to walk ...
-constexpr unsigned long long kSoloEdges = 8192;    // ... and this many entries to visit runs on CTA 0 alone
-constexpr uint32_t kSoloCopy = 4096;         // a publish of at most this many ids is done by CTA 0 alone
+constexpr uint32_t kSoloWalk = 96;           // a sub-round with at most this many unitigs to walk (and no slices) runs on CTA 0 alone
+constexpr unsigned long long kSoloEdges = 8192;
+constexpr uint32_t kSoloCopy = 1024;         // a publish of at most this many ids is done by the leader warp alone
 constexpr uint32_t kStage = 2048;            // discoveries a CTA collects in shared memory before one append to the log
 constexpr int kScanItems = 4;
 constexpr unsigned long long kPeelWatchdogNs = 20ull * 1000000000ull;
@@ -125,6 +126,24 @@ __device__ __forceinline__ unsigned long long pglobal_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+
+// A log entry of a peer is valid as soon as it differs from kLogEmpty (the logs are cleared before the peel and every slot
+// is written once): the length a peer publishes may overtake the entries themselves on the wire, so no fence or
+// acknowledgement round trip stands between copying ids and announcing them.
+constexpr uint32_t kLogEmpty = 0xffffffffu;
+__device__ __forceinline__ uint32_t log_read(const uint32_t *slot, PRankState *st) {
+    uint32_t x = *reinterpret_cast<const volatile uint32_t *>(slot);
+    if (x != kLogEmpty) return x;
+    const unsigned long long t0 = pglobal_ns();
+    uint32_t spins = 0;
+    while ((x = *reinterpret_cast<const volatile uint32_t *>(slot)) == kLogEmpty) {
+        if ((++spins & 1023u) == 0 && (*(volatile uint32_t *)&st->error || pglobal_ns() - t0 > kPeelWatchdogNs)) {
+            atomicCAS(&st->error, 0u, 2u);
+            break;
+        }
+    }
+    return x;
 }
 
 // barrier of one rank's CTAs.  sys_fence: the CTAs stored into peer memory before it, and those stores must be
@@ -294,14 +313,17 @@ __device__ __forceinline__ void walk_stage(const PRank &R, PRankState *st, Stage
     __syncthreads();
     unsigned long long total_new = 0;
     for (int q = 0; q < R.world; ++q) total_new += sg.src_cnt[q];
-    for (unsigned long long c0 = (unsigned long long)cta_w0 * 32ull; c0 < total_new; c0 += (unsigned long long)per_round * 32ull) {
-        const unsigned long long i = c0 + (unsigned long long)warp * 32ull + lane;
+    // unitigs per warp batch: few fresh unitigs are spread over all the warps (a collapsing core peels a few hundred
+    // unitigs with hundreds of neighbours each per generation: one list per warp, not 32)
+    const uint32_t b = (uint32_t)min(max((total_new + nw - 1) / nw, 1ull), 32ull);
+    for (unsigned long long c0 = (unsigned long long)cta_w0 * b; c0 < total_new; c0 += (unsigned long long)per_round * b) {
+        const unsigned long long i = c0 + (unsigned long long)warp * b + lane;
         uint32_t first = 0, len = 0;
-        if (i < total_new) {
+        if (lane < b && i < total_new) {
             unsigned long long off = i;
             int q = 0;
             while (off >= sg.src_cnt[q]) { off -= sg.src_cnt[q]; ++q; }   // which source's log (i < total_new: q stays < world)
-            const uint32_t x = __ldcg(&R.log_local[q][sg.src_lo[q] + off]);
+            const uint32_t x = log_read(&R.log_local[q][sg.src_lo[q] + off], st);
             if (x >= R.n_global) {
                 atomicCAS(&st->error, 0u, 4u);
             } else {
@@ -398,11 +420,18 @@ __device__ __forceinline__ void scan_stage(const PRank &R, PRankState *st, uint3
 }
 
 // The leader (warp 0 of the rank's CTA 0) meets the other ranks: publish the counts, wait, decide.
-__device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, uint32_t t, uint32_t cur, int32_t k, bool scanned) {
+// Lane 0 never stores into peer memory: it is the thread that releases the plan to the rank's other CTAs, and a
+// release (or fence) waits for the calling thread's own outstanding stores -- for stores that crossed NVLink that is
+// a full round trip.  Lane q + 1 talks to rank q.
+__device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, uint32_t t, uint32_t cur, int32_t k, bool scanned,
+                                                bool copy_here, unsigned long long &peer_log_hi, uint32_t &published) {
     const uint32_t lane = lane_id();
     const int world = R.world;
+    const int peer = (int)lane - 1;                 // the rank this lane talks to (lanes 1 .. world)
+    const bool has_peer = peer >= 0 && peer < world;
     const unsigned long long tag = (unsigned long long)t << kTagShift;
     unsigned long long log_len = 0, n_slices = 0;
+    uint32_t pub_lo = 0;
     int32_t lmin = INT32_MAX;
     if (lane == 0) {
         log_len = __ldcg(&st->log_cnt);
@@ -413,9 +442,19 @@ __device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, 
     log_len = __shfl_sync(kFullMask, log_len, 0);
     n_slices = __shfl_sync(kFullMask, n_slices, 0);
     lmin = __shfl_sync(kFullMask, lmin, 0);
-    __threadfence_system();   // the copies of the log this rank made are visible at the peers before the counts
-    if ((int)lane < world) {
-        PeelCtl *dst = R.ctl_peer[lane];
+    pub_lo = published;          // every lane of the leader warp carries it in a register
+    published = (uint32_t)log_len;
+    if (copy_here && world > 1 && lane > 0) {
+        // a short new part of the log: this warp copies it to the peers itself, then announces it -- no barrier, no fence
+        const uint32_t *src = R.log_local[R.rank];
+        for (uint32_t i = pub_lo + (lane - 1u); i < (uint32_t)log_len; i += 31u) {
+            const uint32_t x = __ldcg(&src[i]);
+            for (int p = 0; p < world; ++p)
+                if (p != R.rank) R.log_peer[p][i] = x;
+        }
+    }
+    if (has_peer) {
+        PeelCtl *dst = R.ctl_peer[peer];
         st_relaxed_sys(&dst->w[R.rank][1], tag | n_slices);
         st_relaxed_sys(&dst->w[R.rank][2], tag | (unsigned long long)(uint32_t)lmin);
         st_relaxed_sys(&dst->w[R.rank][0], tag | log_len);
@@ -424,19 +463,18 @@ __device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, 
     const unsigned long long t_wait = pglobal_ns();
     unsigned long long w0 = 0, w1 = 0, w2 = (unsigned long long)(uint32_t)INT32_MAX;
     bool failed = false;
-    if ((int)lane < world) {
+    if (has_peer) {
         const PeelCtl *mine = R.ctl_local;
         uint32_t spins = 0;
         while (true) {
-            w0 = ld_relaxed_sys(&mine->w[lane][0]);
-            w1 = ld_relaxed_sys(&mine->w[lane][1]);
-            w2 = ld_relaxed_sys(&mine->w[lane][2]);
+            w0 = ld_relaxed_sys(&mine->w[peer][0]);
+            w1 = ld_relaxed_sys(&mine->w[peer][1]);
+            w2 = ld_relaxed_sys(&mine->w[peer][2]);
             if ((w0 >> kTagShift) == t && (w1 >> kTagShift) == t && (w2 >> kTagShift) == t) break;
             if ((++spins & 1023u) == 0 && (*(volatile uint32_t *)&st->error || pglobal_ns() - t_wait > kPeelWatchdogNs)) { failed = true; break; }
         }
         w0 &= kValMask; w1 &= kValMask; w2 &= kValMask;
     }
-    __threadfence_system();   // acquire: the peers' log entries are read after their counts
     if (lane == 0) st->prof_ns[3] += pglobal_ns() - t_wait;
     if (__ballot_sync(kFullMask, failed)) {
         if (lane == 0) {
@@ -445,44 +483,26 @@ __device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, 
         }
         return;
     }
-    unsigned long long fresh = 0;
-    if ((int)lane < world) {
-        const unsigned long long before = __ldcg(&st->log_hi[lane]);
-        st->log_lo[lane] = before;
-        st->log_hi[lane] = w0;
-        fresh = w0 - before;
-    }
-    unsigned long long g_fresh = fresh, g_slices = (int)lane < world ? w1 : 0ull, g_total = (int)lane < world ? w0 : 0ull;
-    uint32_t g_min = (int)lane < world ? (uint32_t)w2 : (uint32_t)INT32_MAX;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        g_fresh += __shfl_xor_sync(kFullMask, g_fresh, o);
-        g_slices += __shfl_xor_sync(kFullMask, g_slices, o);
-        g_total += __shfl_xor_sync(kFullMask, g_total, o);
-        g_min = min(g_min, __shfl_xor_sync(kFullMask, g_min, o));
-    }
-    __threadfence();   // every lane's stores to log_lo / log_hi are ordered before lane 0's release of the plan
-    __syncwarp();
-    // how much is there to walk HERE: the fresh unitigs' local neighbour lists (exact when there are few of them)
-    unsigned long long my_entries = ~0ull;
-    if (g_fresh <= kSoloWalk && n_slices == 0) {
-        unsigned long long e = 0;
-        for (unsigned long long i = lane; i < g_fresh; i += 32) {
-            unsigned long long off = i;
-            int q = 0;
-            while (true) {
-                const unsigned long long cq = st->log_hi[q] - st->log_lo[q];
-                if (off < cq) break;
-                off -= cq;
-                ++q;
-            }
-            const uint32_t x = __ldcg(&R.log_local[q][st->log_lo[q] + off]);
-            if (x < R.n_global) e += R.nbr_ptr[x + 1] - R.nbr_ptr[x];
+    // lane 0 records the new log lengths itself (its release of the plan then covers them); the previous lengths live in
+    // the registers of the lanes that talk to the peers: nothing is loaded here
+    const unsigned long long my_before = peer_log_hi;
+    if (has_peer) peer_log_hi = w0;
+    unsigned long long g_fresh = 0, g_slices = 0, g_total = 0;
+    uint32_t g_min = (uint32_t)INT32_MAX;
+    for (int q = 0; q < world; ++q) {
+        const unsigned long long hi = __shfl_sync(kFullMask, w0, q + 1);
+        const unsigned long long before = __shfl_sync(kFullMask, my_before, q + 1);
+        g_slices += __shfl_sync(kFullMask, w1, q + 1);
+        g_min = min(g_min, (uint32_t)__shfl_sync(kFullMask, w2, q + 1));
+        g_total += hi;
+        g_fresh += hi - before;
+        if (lane == 0) {
+            st->log_lo[q] = before;
+            st->log_hi[q] = hi;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(kFullMask, e, o);
-        my_entries = e;
     }
+    // few fresh unitigs and nothing pending: this rank walks them on CTA 0 alone (their lists are at most kSliceLen long)
+    const unsigned long long my_entries = (g_fresh <= kSoloWalk && n_slices == 0) ? 0ull : ~0ull;
     if (lane == 0) {
         uint32_t flags = (my_entries <= kSoloEdges) ? 0u : kWalkFull;
         st->subrounds = t;
@@ -501,7 +521,6 @@ __device__ __forceinline__ void leader_exchange(const PRank &R, PRankState *st, 
         } else if (!(flags & kWalkFull)) {
             st->solo_subrounds += 1;
         }
-        __threadfence();
         st_rel_gpu(&st->plan_b[t % kPlanRing], ((unsigned long long)t << 8) | flags);
     }
 }
@@ -526,6 +545,8 @@ __global__ void __launch_bounds__(kPThreads, 2) ppeel_kernel(const PRank *ranks,
     uint32_t n_alive = R.n_local;
     if (tid == 0) s_stage.n = 0;
     __syncthreads();
+    unsigned long long peer_log_hi = 0;   // leader warp, lane q + 1: length of rank q's log at the last exchange
+    uint32_t published = 0;               // leader warp: length of the own log at the last exchange
 
     const bool prof = leader_cta && tid == 0;
     unsigned long long tp = prof ? pglobal_ns() : 0ull;
@@ -552,7 +573,6 @@ __global__ void __launch_bounds__(kPThreads, 2) ppeel_kernel(const PRank *ranks,
         if (leader_cta && tid == 0) {
             const uint32_t fresh = __ldcg(&st->log_cnt) - __ldcg(&st->published);
             const uint32_t mode = (R.world > 1 && fresh > kSoloCopy) ? kCopyFull : 0u;
-            __threadfence();
             st_rel_gpu(&st->plan_a[t % kPlanRing], ((unsigned long long)t << 8) | mode);
         }
         const uint32_t mode_a = wait_plan(&st->plan_a[t % kPlanRing], t, st, &s_bcast);
@@ -561,17 +581,12 @@ __global__ void __launch_bounds__(kPThreads, 2) ppeel_kernel(const PRank *ranks,
         // ---- publish
         if (mode_a & kCopyFull) {
             publish_stage(R, st, cta * kPThreads + tid, R.ctas * kPThreads);
-            rank_barrier(st, R.ctas, bar_gen, true);
+            rank_barrier(st, R.ctas, bar_gen, false);
             if (prof) { st->full_copy += 1; st->prof_ns[6] += pglobal_ns() - tp; }
-        } else if (leader_cta) {
-            if (R.world > 1) publish_stage(R, st, tid, kPThreads);
-            __syncthreads();
-            if (tid == 0) __threadfence_system();
-            __syncthreads();
         }
         KG_PROF(2);
-        // ---- exchange
-        if (leader_cta && warp == 0) leader_exchange(R, st, t, cur, k, scan);
+        // ---- exchange (a short publish is done by the leader warp itself)
+        if (leader_cta && warp == 0) leader_exchange(R, st, t, cur, k, scan, !(mode_a & kCopyFull), peer_log_hi, published);
         const uint32_t flags = wait_plan(&st->plan_b[t % kPlanRing], t, st, &s_bcast);
         KG_PROF(4);
         // ---- walk
@@ -631,6 +646,7 @@ int dist_peel(kombgpu_dist_graph *g) {
     KG_TRY(sym_alloc(c, (size_t)world * log_cap, &logs, &logs_peers));
     KG_TRY(sym_alloc(c, 1, &ctl, &ctl_peers));
     KG_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(PeelCtl), ctx->stream));
+    KG_CUDA(ctx, cudaMemsetAsync(logs, 0xff, (size_t)world * log_cap * sizeof(uint32_t), ctx->stream));   // kLogEmpty
 
     // per-rank lists and state
     DevBuf<int32_t> work;
