@@ -24,6 +24,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kombgpu.h"
@@ -128,6 +129,23 @@ class Kgraph {
     // results of the whole path, fetched in one overlapped call (kombgpu_graph_results) by readEdgeList
     std::unique_ptr<PinnedArray<uint64_t>> _efp;   // edge list in CSR form: forward offsets per source + targets
     std::unique_ptr<PinnedArray<uint32_t>> _ev;
+    // multi-GPU (KOMB_GPU_DEVICES=0,1,...): one rank per device, a host thread per rank; each rank's share of the results
+    struct RankOut {
+        uint32_t v_lo = 0, n_local = 0;
+        uint64_t n_fwd = 0;
+        std::vector<uint64_t> fwd_ptr;
+        std::vector<uint32_t> v;
+        std::vector<int32_t> deg, core;
+        std::vector<double> score;
+        int rc = KOMBGPU_OK;
+        std::string err;
+    };
+    std::vector<int> _devices;
+    std::vector<RankOut> _ranks;
+    uint64_t _m_multi = 0;
+    int32_t _max_core_multi = 0;
+    double _max_score_multi = 0.0;
+    bool multi() const { return _devices.size() > 1; }
     std::unique_ptr<PinnedArray<int32_t>> _deg, _core;
     std::unique_ptr<PinnedArray<double>> _score;
 
@@ -144,8 +162,9 @@ class Kgraph {
     }
 
    public:
-    Kgraph(uint32_t threads, uint64_t readlength, int device, int key_mode)
-        : _threads(threads ? threads : 1), _readlength(readlength), _key_mode(key_mode), _device(device) {
+    Kgraph(uint32_t threads, uint64_t readlength, int device, int key_mode, std::vector<int> devices = {})
+        : _threads(threads ? threads : 1), _readlength(readlength), _key_mode(key_mode), _device(device), _devices(std::move(devices)) {
+        if (multi()) { timing_mark("start"); return; }   // every rank's thread creates its own context (runMulti)
         // Creating the CUDA context costs seconds on a box without the persistence daemon (1.9 - 4.1 s measured on
         // the B200 boxes, against 0.75 s for everything else on a 2.5 M-hit SAM pair): do it on a helper thread
         // while the SAM files are tokenised and interned on the host; generateGraph is the first to need it.
@@ -219,7 +238,92 @@ class Kgraph {
         timing_mark("intern keys + names");
     }
 
+    // The whole device phase over several GPUs: hits split by read range (a read's hits stay together), one host
+    // thread per rank; the ranks talk through peer memory inside libkombgpu (include/kombgpu.h, peer-memory path).
+    void runMulti(HitTable &hits) {
+        const int world = (int)_devices.size();
+        const uint32_t n = (uint32_t)hits.names.size();
+        const size_t h = hits.read_key.size();
+        uint32_t n_reads = 0;
+        for (size_t i = 0; i < h; ++i) n_reads = std::max(n_reads, hits.read_key[i] + 1);
+        _ranks.assign(world, RankOut());
+        void *group_slot = nullptr;
+        // phase 1: the contexts (seconds each on a cold driver, so in parallel); nobody enters a collective before all exist
+        std::vector<kombgpu_ctx *> ctxs(world, nullptr);
+        {
+            std::vector<std::thread> tc;
+            for (int r = 0; r < world; ++r)
+                tc.emplace_back([&, r]() {
+                    const int rc = kombgpu_ctx_create(_devices[r], &ctxs[r]);
+                    if (rc != KOMBGPU_OK) { _ranks[r].rc = rc; _ranks[r].err = std::string("kombgpu_ctx_create: ") + kombgpu_last_error(nullptr); }
+                });
+            for (auto &t : tc) t.join();
+            bool ok = true;
+            for (int r = 0; r < world; ++r)
+                if (_ranks[r].rc != KOMBGPU_OK) {
+                    std::cerr << "komb2: cannot use CUDA device " << _devices[r] << ": " << _ranks[r].err << std::endl;
+                    ok = false;
+                }
+            if (!ok) {
+                for (auto *c : ctxs) if (c) kombgpu_ctx_destroy(c);
+                exit(EXIT_FAILURE);
+            }
+        }
+        timing_mark("kombgpu_ctx_create (all devices)");
+        std::vector<std::thread> th;
+        for (int r = 0; r < world; ++r)
+            th.emplace_back([&, r]() {
+                RankOut &o = _ranks[r];
+                kombgpu_ctx *ctx = ctxs[r];
+                kombgpu_comm *comm = nullptr;
+                kombgpu_dist_graph *g = nullptr;
+                auto fail = [&](int rc, const char *what) {
+                    o.rc = rc;
+                    o.err = std::string(what) + ": " + kombgpu_last_error(ctx);
+                    if (comm) kombgpu_comm_abort(comm);
+                };
+                int rc = kombgpu_comm_create_local(ctx, r, world, &group_slot, 0, &comm);
+                if (rc != KOMBGPU_OK) fail(rc, "kombgpu_comm_create_local");
+                if (rc == KOMBGPU_OK) {
+                    // this rank's reads: ids [lo, hi)
+                    const uint32_t lo = (uint32_t)((uint64_t)n_reads * r / world), hi = (uint32_t)((uint64_t)n_reads * (r + 1) / world);
+                    std::vector<uint32_t> rk, ut;
+                    for (size_t i = 0; i < h; ++i)
+                        if (hits.read_key[i] >= lo && hits.read_key[i] < hi) { rk.push_back(hits.read_key[i]); ut.push_back(hits.unitig[i]); }
+                    rc = kombgpu_dist_build_hits(comm, rk.data(), ut.data(), rk.size(), n, &g);
+                    if (rc != KOMBGPU_OK) fail(rc, "kombgpu_dist_build_hits");
+                }
+                if (rc == KOMBGPU_OK && (rc = kombgpu_dist_coreness(g)) != KOMBGPU_OK) fail(rc, "kombgpu_dist_coreness");
+                if (rc == KOMBGPU_OK && (rc = kombgpu_dist_corea(g, _key_mode)) != KOMBGPU_OK) fail(rc, "kombgpu_dist_corea");
+                if (rc == KOMBGPU_OK) {
+                    kombgpu_dist_stats st;
+                    kombgpu_dist_graph_stats(g, &st);
+                    o.v_lo = st.v_lo; o.n_local = st.n_local; o.n_fwd = st.n_fwd_local;
+                    o.fwd_ptr.resize((size_t)o.n_local + 1); o.v.resize(o.n_fwd);
+                    o.deg.resize(o.n_local); o.core.resize(o.n_local); o.score.resize(o.n_local);
+                    rc = kombgpu_dist_graph_results(g, o.deg.data(), o.core.data(), o.score.data());
+                    if (rc == KOMBGPU_OK) rc = kombgpu_dist_graph_edges_csr(g, o.fwd_ptr.data(), o.v.data());
+                    if (rc != KOMBGPU_OK) fail(rc, "kombgpu_dist_graph_results");
+                    if (r == 0) {
+                        _m_multi = st.n_edges_global;
+                        kombgpu_dist_graph_summary(g, &_max_core_multi, &_max_score_multi);
+                    }
+                }
+                if (g) kombgpu_dist_graph_destroy(g);
+                if (comm) kombgpu_comm_destroy(comm);
+                if (ctx) kombgpu_ctx_destroy(ctx);
+            });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < world; ++r)
+            if (_ranks[r].rc != KOMBGPU_OK) {
+                std::cerr << "komb2: rank " << r << " (device " << _devices[r] << "): " << _ranks[r].err << " (" << _ranks[r].rc << ")" << std::endl;
+                exit(EXIT_FAILURE);
+            }
+        timing_mark("multi-GPU build + peel + CORE-A + results");
+    }
+
     void generateGraph(HitTable &hits) {
+        if (multi()) { runMulti(hits); return; }
         waitForDevice();
         int rc = kombgpu_build_graph(_ctx, hits.read_key.data(), hits.unitig.data(), hits.read_key.size(),
                                      (uint32_t)hits.names.size(), &_graph);
@@ -234,6 +338,36 @@ class Kgraph {
         auto begin_graph = std::chrono::steady_clock::now();
         uint32_t n = 0;
         uint64_t m = 0;
+        if (multi()) {
+            // the ranks' slices of the canonical edge list, in rank order, ARE the sorted list
+            n = (uint32_t)hits.names.size();
+            m = _m_multi;
+            for (const RankOut &o : _ranks) {
+                const uint64_t *fp = o.fwd_ptr.data();
+                write_row_blocks(ef, o.n_fwd, 24, (int)_threads, [&](char *p, size_t lo, size_t hi) {
+                    size_t x = (size_t)(std::upper_bound(fp, fp + o.n_local + 1, (uint64_t)lo) - fp) - 1;
+                    for (size_t i = lo; i < hi; ++i) {
+                        while (fp[x + 1] <= i) ++x;
+                        p = put_u64(p, (uint64_t)o.v_lo + x); *p++ = '\t';
+                        p = put_u64(p, o.v[i]); *p++ = '\n';
+                    }
+                    return p;
+                });
+            }
+            fclose(ef);
+            timing_mark("write edgelist.txt");
+            fprintf(stdout, "\nTime elapsed for initializing igraph graph: %.3f s\n", seconds_since(begin_graph));
+            fprintf(stdout, "\nTime elapsed for simplifying graph: %.3f s\n", 0.0);
+            fprintf(stdout, "GraphInfo...\n\tNumber of vertices: %d\n", (int)n);
+            fprintf(stdout, "\tNumber of edges: %d\n", (int)m);
+            FILE *uf2 = fopen(inputUnitigs.c_str(), "r");
+            if (uf2 == nullptr) fileNotFoundError(inputUnitigs);
+            fclose(uf2);
+            auto begin_kcore2 = std::chrono::steady_clock::now();
+            runCore(dir, hits);
+            fprintf(stdout, "\nTime elapsed doing K-core decomposition: %.3f s\n", seconds_since(begin_kcore2));
+            return;
+        }
         kombgpu_graph_counts(_graph, &n, &m);
         // one call fetches everything the three output files need; the edge-list download (CSR form: offsets per
         // source + targets, half the bytes of two id arrays) overlaps the peel
@@ -275,7 +409,16 @@ class Kgraph {
     void runCore(const std::string &dir, HitTable &hits) {
         const std::string kcore_file = dir + "/kcore.tsv";
         const uint32_t n = (uint32_t)hits.names.size();
-        PinnedArray<int32_t> &deg = *_deg, &core = *_core;  // fetched by readEdgeList
+        // fetched by readEdgeList (one GPU) or runMulti (every rank's slice)
+        std::vector<int32_t> deg_all, core_all;
+        if (multi()) {
+            deg_all.resize(n); core_all.resize(n);
+            for (const RankOut &o : _ranks) {
+                std::copy(o.deg.begin(), o.deg.end(), deg_all.begin() + o.v_lo);
+                std::copy(o.core.begin(), o.core.end(), core_all.begin() + o.v_lo);
+            }
+        }
+        const int32_t *deg = multi() ? deg_all.data() : _deg->data(), *core = multi() ? core_all.data() : _core->data();
         FILE *kcf = fopen(kcore_file.c_str(), "w+");
         if (kcf == nullptr) fileNotFoundError(kcore_file);
         fprintf(kcf, "#VID\tName\tCoreness\tDegree\n");
@@ -293,11 +436,21 @@ class Kgraph {
     }
 
     void anomalyDetection(const std::string &dir, bool weight) {
-        const uint32_t n = [&] { uint32_t nn = 0; kombgpu_graph_counts(_graph, &nn, nullptr); return nn; }();
-        PinnedArray<double> &score = *_score;  // fetched by readEdgeList
+        uint32_t n = 0;
+        std::vector<double> score_all;
         int32_t max_core = 0;
         double max_score = 0.0;
-        kombgpu_graph_summary(_graph, &max_core, &max_score);
+        if (multi()) {
+            for (const RankOut &o : _ranks) n += o.n_local;
+            score_all.resize(n);
+            for (const RankOut &o : _ranks) std::copy(o.score.begin(), o.score.end(), score_all.begin() + o.v_lo);
+            max_core = _max_core_multi;
+            max_score = _max_score_multi;
+        } else {
+            kombgpu_graph_counts(_graph, &n, nullptr);
+            kombgpu_graph_summary(_graph, &max_core, &max_score);
+        }
+        const double *score = multi() ? score_all.data() : _score->data();  // fetched by readEdgeList / runMulti
         const double dense_ratio = (double)(max_core / 2);  // integer division, like CombineCoreA.h:24
         fprintf(stdout, "Dense Ratio: %f\n", n ? dense_ratio : 0.0);
         if (weight) {
@@ -314,7 +467,8 @@ class Kgraph {
             timing_mark("write CoreA_anomaly.txt");
         }
         _efp.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();
-        kombgpu_graph_destroy(_graph);
+        _ranks.clear();
+        if (_graph) kombgpu_graph_destroy(_graph);
         _graph = nullptr;
         timing_mark("free pinned + graph");
     }

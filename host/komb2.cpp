@@ -5,6 +5,8 @@
 // KOMB.py (reference KOMB.py:435-462) drives it unchanged.
 //
 // Environment: KOMB_GPU_DEVICE (CUDA ordinal, default 0);
+//              KOMB_GPU_DEVICES=0,1,... (two or more ordinals: the graph is partitioned over these GPUs of the node,
+//              one host thread per GPU, peer-memory path of libkombgpu; same output files);
 //              KOMB_COREA_KEY=exact64 selects the overflow-free CORE-A key
 //              (default "ref32" reproduces the reference's int32 wrap, quirk Q5).
 #include <omp.h>
@@ -14,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "cli.hpp"
 #include "kgraph.hpp"
@@ -30,7 +33,18 @@ int main(int argc, const char **argv) {
     const int device = dev_env ? atoi(dev_env) : 0;
     const int key_mode = (key_env && strcmp(key_env, "exact64") == 0) ? KOMBGPU_KEY_EXACT64 : KOMBGPU_KEY_REF32;
 
-    komb::Kgraph kg((uint32_t)opt.threads, (uint64_t)opt.readlen, device, key_mode);
+    std::vector<int> devices;
+    if (const char *list = getenv("KOMB_GPU_DEVICES")) {
+        for (const char *p = list; *p;) {
+            char *end = nullptr;
+            const long d = strtol(p, &end, 10);
+            if (end == p) break;
+            devices.push_back((int)d);
+            p = *end == ',' ? end + 1 : end;
+        }
+    }
+
+    komb::Kgraph kg((uint32_t)opt.threads, (uint64_t)opt.readlen, device, key_mode, devices);
     komb::HitTable hits;
     komb::MappedFile sam1, sam2;  // the hit table points into these until the ids exist
     auto begin_komb = std::chrono::steady_clock::now();

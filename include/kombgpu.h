@@ -207,6 +207,18 @@ int kombgpu_graph_results_csr(kombgpu_graph *g, int key_mode, uint64_t *fwd_ptr,
 int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uint32_t *n_vertices, uint64_t *n_edges,
                                double *density);
 
+/* The maximal core and the trussness of its edges (needs kombgpu_coreness): the induced subgraph of the unitigs
+ * whose coreness is the maximum, igraph_trussness of every edge of it (the largest k such that the edge lies in a
+ * k-truss; 2 for an edge in no triangle) and the unitigs on the edges of maximal trussness -- what the reference's
+ * Kgraph::runTruss computes before it writes truss_unitigs.fasta (src/graph.cpp:486-563; runCore collects the
+ * maximal core at :470-476; the call is commented out at :478).  Computed once per graph, cached. */
+int kombgpu_graph_max_core_truss(kombgpu_graph *g, uint32_t *n_core_vertices, uint64_t *n_core_edges,
+                                 int32_t *max_trussness, uint32_t *n_truss_vertices);
+/* Edges of the maximal core (original unitig ids, u < v, ascending) with their trussness; n_core_edges entries each. */
+int kombgpu_graph_max_core_edges(const kombgpu_graph *g, uint32_t *u, uint32_t *v, int32_t *trussness);
+/* The unitigs on edges of maximal trussness (original ids, ascending); n_truss_vertices entries. */
+int kombgpu_graph_truss_vertices(const kombgpu_graph *g, uint32_t *vids);
+
 /* The whole path in one call, host buffers in and out: what komb2 does between readSAM and its three writers
  * (getEdgeInfo ... anomalyDetection, src/komb2.cpp:104-132).  Same results as kombgpu_build_graph followed by
  * kombgpu_graph_results; the difference is scheduling: the edge list is final half-way through the build (the CSR
@@ -363,6 +375,11 @@ int kombgpu_dist_build_hits_dev(kombgpu_comm *comm, const uint32_t *read_key_dev
                                 uint64_t n_hits, uint32_t n_vertices_global, kombgpu_dist_graph **out);
 int kombgpu_dist_build_pairs_dev(kombgpu_comm *comm, const uint32_t *u_dev, const uint32_t *v_dev, uint64_t n_pairs,
                                  uint32_t n_vertices_global, kombgpu_dist_graph **out);
+/* The same with HOST pointers (the rank's share is uploaded first): for hosts without CUDA headers (komb2). */
+int kombgpu_dist_build_hits(kombgpu_comm *comm, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits,
+                            uint32_t n_vertices_global, kombgpu_dist_graph **out);
+int kombgpu_dist_build_pairs(kombgpu_comm *comm, const uint32_t *u, const uint32_t *v, uint64_t n_pairs,
+                             uint32_t n_vertices_global, kombgpu_dist_graph **out);
 int kombgpu_dist_coreness(kombgpu_dist_graph *g);               /* igraph_coreness over all ranks */
 int kombgpu_dist_corea(kombgpu_dist_graph *g, int key_mode);    /* CoreA::getAnomalyScore over all ranks */
 void kombgpu_dist_graph_destroy(kombgpu_dist_graph *g);

@@ -88,6 +88,9 @@ SIGNATURES = {
                                      c_void_p, c_void_p, POINTER(c_void_p)]),
     "kombgpu_graph_densest_core": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint64), POINTER(c_double)]),
     "kombgpu_graph_analyse": (c_int, [c_void_p, c_int]),
+    "kombgpu_graph_max_core_truss": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32), POINTER(c_uint32)]),
+    "kombgpu_graph_max_core_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kombgpu_graph_truss_vertices": (c_int, [c_void_p, c_void_p]),
     "kombgpu_graph_results": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kombgpu_graph_stats": (c_int, [c_void_p, POINTER(Stats)]),
     "kombgpu_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
@@ -115,6 +118,8 @@ SIGNATURES = {
     "kombgpu_comm_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_uint64)]),
     "kombgpu_dist_build_hits_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_dist_build_pairs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_dist_build_hits": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
+    "kombgpu_dist_build_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_dist_coreness": (c_int, [c_void_p]),
     "kombgpu_dist_corea": (c_int, [c_void_p, c_int]),
     "kombgpu_dist_graph_destroy": (None, [c_void_p]),

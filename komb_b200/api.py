@@ -321,6 +321,18 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_densest_core(self._h, byref(k), byref(nv), byref(ne), byref(d)))
         return {"k": k.value, "n_vertices": nv.value, "n_edges": ne.value, "density": d.value}
 
+    def max_core_truss(self) -> dict:
+        """Maximal core + trussness of its edges (kombgpu_graph_max_core_truss, reference Kgraph::runTruss): sizes, the
+        induced edges (original ids) with their trussness, and the unitigs on edges of maximal trussness."""
+        nc, mc, tm, nt = c_uint32(), c_uint64(), c_int32(), c_uint32()
+        self._ctx._check(self._lib.kombgpu_graph_max_core_truss(self._h, byref(nc), byref(mc), byref(tm), byref(nt)))
+        u, v, tr = np.empty(mc.value, np.uint32), np.empty(mc.value, np.uint32), np.empty(mc.value, np.int32)
+        self._ctx._check(self._lib.kombgpu_graph_max_core_edges(self._h, _ptr(u), _ptr(v), _ptr(tr)))
+        tv = np.empty(nt.value, np.uint32)
+        self._ctx._check(self._lib.kombgpu_graph_truss_vertices(self._h, _ptr(tv)))
+        return {"n_core_vertices": nc.value, "n_core_edges": mc.value, "max_trussness": tm.value, "u": u, "v": v, "trussness": tr,
+                "truss_vertices": tv}
+
     def stats(self) -> dict:
         st = Stats()
         self._ctx._check(self._lib.kombgpu_graph_stats(self._h, byref(st)))

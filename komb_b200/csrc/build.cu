@@ -292,15 +292,47 @@ __global__ void __launch_bounds__(kThreads) swap_pack_kernel(const uint64_t *__r
     }
 }
 
-// keys sorted by their high word x in [0, n): start[x] = first index whose high
-// word is >= x, for x in [0, n]  (start[n] = count).  No atomics: thread i fills
-// the ids between its predecessor's high word and its own.
-__global__ void __launch_bounds__(kThreads) row_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t count,
-                                                              uint32_t n, uint32_t *__restrict__ start) {
+// keys sorted by their high word, which lies in [base, base + n_rows): start[x] = first index whose high word is
+// >= base + x, for x in [0, n_rows]  (start[n_rows] = count).  No atomics on the result: thread i fills the rows between
+// its predecessor's and its own -- but only short gaps; a long run of empty rows (a rank of the partitioned path sees
+// only the neighbourhood of its own id range; an edge list may leave whole id ranges without edges) is recorded and
+// filled by a whole CTA in a second kernel, so one thread never writes millions of entries.
+// *err (optional) is raised when a key lies outside [base, base + n_rows) or its low word is >= lo_bound.
+constexpr int64_t kGapShort = 32;
+struct RowGap {
+    uint32_t lo, hi, val;   // start[lo .. hi] = val
+};
+__global__ void __launch_bounds__(kThreads) row_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t count, uint32_t base,
+                                                              uint32_t n_rows, uint32_t lo_bound, uint32_t *__restrict__ start,
+                                                              RowGap *__restrict__ gaps, uint32_t *__restrict__ n_gaps, uint32_t *__restrict__ err) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += (uint64_t)gridDim.x * blockDim.x) {
-        int64_t cur = i < count ? (int64_t)(keys[i] >> 32) : (int64_t)n;
-        int64_t prev = i > 0 ? (int64_t)(keys[i - 1] >> 32) : -1;
-        for (int64_t x = prev + 1; x <= cur; ++x) start[x] = (uint32_t)i;
+        int64_t cur = (int64_t)n_rows, prev = -1;
+        if (i < count) {
+            const uint64_t k = keys[i];
+            cur = (int64_t)(uint32_t)(k >> 32) - (int64_t)base;
+            if (cur < 0 || cur >= (int64_t)n_rows || (uint32_t)k >= lo_bound) {
+                if (err) atomicExch(err, 2u);
+                cur = (int64_t)n_rows;
+            }
+        }
+        if (i > 0) {
+            prev = (int64_t)(uint32_t)(keys[i - 1] >> 32) - (int64_t)base;
+            if (prev < 0 || prev >= (int64_t)n_rows) prev = (int64_t)n_rows;
+        }
+        if (cur - prev > kGapShort) {
+            const uint32_t g = atomicAdd(n_gaps, 1u);
+            gaps[g] = RowGap{(uint32_t)(prev + 1), (uint32_t)cur, (uint32_t)i};
+        } else {
+            for (int64_t x = prev + 1; x <= cur; ++x) start[x] = (uint32_t)i;
+        }
+    }
+}
+__global__ void __launch_bounds__(kThreads) row_gaps_kernel(const RowGap *__restrict__ gaps, const uint32_t *__restrict__ n_gaps,
+                                                            uint32_t *__restrict__ start) {
+    const uint32_t n = *n_gaps;
+    for (uint32_t g = blockIdx.x; g < n; g += gridDim.x) {
+        const RowGap gp = gaps[g];
+        for (uint64_t x = (uint64_t)gp.lo + threadIdx.x; x <= gp.hi; x += blockDim.x) start[x] = gp.val;
     }
 }
 
@@ -616,10 +648,24 @@ int pairs_to_keys(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64
     return KOMBGPU_OK;
 }
 
+int row_starts(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, uint32_t base, uint32_t n_rows, uint32_t lo_bound, uint32_t *start,
+               uint32_t *err_dev) {
+    // a gap longer than kGapShort rows is recorded: at most n_rows / kGapShort + 1 of them
+    DevBuf<RowGap> gaps;
+    DevBuf<uint32_t> n_gaps(ctx, 1);
+    KG_ALLOC(ctx, gaps, (size_t)n_rows / (size_t)kGapShort + 2);
+    if (!n_gaps) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(n_gaps.p, 0, sizeof(uint32_t), ctx->stream));
+    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(count + 1, kThreads), 148u * 16u), kThreads, 0, keys, count, base, n_rows, lo_bound, start,
+              gaps.p, n_gaps.p, err_dev);
+    KG_LAUNCH(ctx, row_gaps_kernel, 148u * 4u, kThreads, 0, gaps.p, n_gaps.p, start);
+    return KOMBGPU_OK;
+}
+
 int forward_index(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t E, uint32_t n, uint32_t **fwd_start_out) {
     DevBuf<uint32_t> fwd_start;
     KG_ALLOC(ctx, fwd_start, (size_t)n + 1);
-    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, edges, E, n, fwd_start.p);
+    KG_TRY(row_starts(ctx, edges, E, 0u, n, 0xffffffffu, fwd_start.p, nullptr));
     *fwd_start_out = fwd_start.take();
     return KOMBGPU_OK;
 }
@@ -637,7 +683,7 @@ int csr_from_edges(kombgpu_ctx *ctx, DevBuf<uint64_t> &edges, uint64_t E, uint32
     KG_ALLOC(ctx, back_start, (size_t)n + 1);
     if (!g->fwd_start) KG_TRY(forward_index(ctx, edges.p, E, n, &g->fwd_start));   // kept: the CSR form of the edge list
     const uint32_t *fwd_start_p = g->fwd_start;
-    KG_LAUNCH(ctx, row_bounds_kernel, min(grid_for(E + 1, kThreads), 148u * 16u), kThreads, 0, swapped, E, n, back_start.p);
+    KG_TRY(row_starts(ctx, swapped, E, 0u, n, 0xffffffffu, back_start.p, nullptr));
 
     DevBuf<uint64_t> row_ptr;
     DevBuf<int32_t> deg, max_deg(ctx, 1);
@@ -759,6 +805,7 @@ int build_from_hits(kombgpu_ctx *ctx, const uint32_t *read_key, const uint32_t *
 void graph_release(kombgpu_graph *g) {
     if (!g || !g->ctx) return;
     kombgpu_ctx *ctx = g->ctx;
+    truss_release(g);
     if (g->edges) ws_free(ctx, g->edges);
     if (g->fwd_start) ws_free(ctx, g->fwd_start);
     if (g->mult) ws_free(ctx, g->mult);

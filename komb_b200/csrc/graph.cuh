@@ -19,6 +19,15 @@ struct kombgpu_graph {
     double max_score = 0.0;
     bool has_core = false, has_score = false;
     kombgpu_stats st{};
+    // maximal core + trussness of its edges (truss.cu), computed on demand
+    bool has_truss = false;
+    uint32_t tr_n_core = 0, tr_n_vertices = 0;
+    uint64_t tr_m = 0;
+    int32_t tr_max = 0;
+    uint32_t *tr_core_vid = nullptr;   // [tr_n_core] original ids of the maximal core, ascending
+    uint64_t *tr_edges = nullptr;      // [tr_m] induced edges, compact ids (a << 32 | b), canonical order
+    int32_t *tr_truss = nullptr;       // [tr_m]
+    uint32_t *tr_vertices = nullptr;   // [tr_n_vertices] original ids of the unitigs on edges of maximal trussness
 };
 
 namespace kg {
@@ -41,6 +50,11 @@ int pairs_to_keys(kombgpu_ctx *ctx, const uint32_t *u, const uint32_t *v, uint64
 // sorted canonical keys (duplicates and loops in) -> unique simple edges (+ optional multiplicities)
 int unique_edges(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, DevBuf<uint64_t> &edges, uint64_t *n_edges,
                  DevBuf<uint32_t> *mult);
+// keys sorted by high word in [base, base + n_rows): start[x] = first index whose high word is >= base + x, x in [0, n_rows];
+// long runs of empty rows are filled by whole CTAs.  *err_dev (optional) is set to 2 when a key is out of range or its
+// low word is >= lo_bound.
+int row_starts(kombgpu_ctx *ctx, const uint64_t *keys, uint64_t count, uint32_t base, uint32_t n_rows, uint32_t lo_bound, uint32_t *start,
+               uint32_t *err_dev);
 // fwd_start[x] = first edge whose source is >= x, x in [0, n]  (the edge list is sorted by source)
 int forward_index(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t n_edges, uint32_t n, uint32_t **fwd_start_out);
 int swapped_sorted(kombgpu_ctx *ctx, const uint64_t *edges, uint64_t n_edges, uint32_t n_vertices, DevBuf<uint64_t> &a,
@@ -63,5 +77,6 @@ int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint
                  double *max_score_host);
 
 void graph_release(kombgpu_graph *g);
+void truss_release(kombgpu_graph *g);   // truss.cu
 
 }  // namespace kg

@@ -129,26 +129,6 @@ __global__ void __launch_bounds__(kThreads) swap_edges_kernel(const uint64_t *__
     }
 }
 
-// keys sorted by high word in [base, base + n_rows): start[x] = first index whose high word is >= base + x, x in [0, n_rows].
-// *err is raised when a key lies outside the range (a mis-routed entry must not write past the arrays).
-__global__ void __launch_bounds__(kThreads) row_bounds_checked_kernel(const uint64_t *__restrict__ keys, uint64_t count, uint32_t base,
-                                                                      uint32_t n_rows, uint32_t n_global, uint32_t *__restrict__ start,
-                                                                      uint32_t *__restrict__ err) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += (uint64_t)gridDim.x * blockDim.x) {
-        int64_t cur = (int64_t)n_rows, prev = -1;
-        if (i < count) {
-            const uint64_t k = keys[i];
-            cur = (int64_t)(uint32_t)(k >> 32) - (int64_t)base;
-            if (cur < 0 || cur >= (int64_t)n_rows || (uint32_t)k >= n_global) { atomicExch(err, 2u); cur = (int64_t)n_rows; }
-        }
-        if (i > 0) {
-            prev = (int64_t)(uint32_t)(keys[i - 1] >> 32) - (int64_t)base;
-            if (prev < 0 || prev >= (int64_t)n_rows) prev = (int64_t)n_rows;
-        }
-        for (int64_t x = prev + 1; x <= cur; ++x) start[x] = (uint32_t)i;
-    }
-}
-
 // the local adjacency entries keyed by the neighbour: entry i < n_fwd is the forward edge (u, v) -> (v << 32 | u - v_lo);
 // entry n_fwd + j is arrival j ((u - v_lo) << 32 | w) -> (w << 32 | u - v_lo), and counts one backward neighbour of u
 __global__ void __launch_bounds__(kThreads) nbr_keys_kernel(const uint64_t *__restrict__ edges, uint64_t n_fwd, const uint64_t *__restrict__ back,
@@ -344,8 +324,7 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     KG_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(deg.p, 0, (size_t)(n_local ? n_local : 1) * sizeof(int32_t), ctx->stream));
-    KG_LAUNCH(ctx, row_bounds_checked_kernel, min(grid_for(n_fwd + 1, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, g->v_lo, n_local,
-              n_global, fwd_start.p, d_err.p);
+    KG_TRY(row_starts(ctx, edges.p, n_fwd, g->v_lo, n_local, n_global, fwd_start.p, d_err.p));
     if (n_dir)
         KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
                   n_global, keys_a.p, deg.p, d_err.p);
@@ -360,8 +339,7 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     g->st.ms_build_sort += split.lap();
     KG_ALLOC(ctx, nbr_ptr, (size_t)n_global + 1);
     KG_ALLOC(ctx, nbr, n_dir);
-    KG_LAUNCH(ctx, row_bounds_checked_kernel, min(grid_for(n_dir + 1, kThreads), 148u * 16u), kThreads, 0, nsorted, n_dir, 0u, n_global,
-              n_local ? n_local : 1u, nbr_ptr.p, d_err.p);
+    KG_TRY(row_starts(ctx, nsorted, n_dir, 0u, n_global, n_local ? n_local : 1u, nbr_ptr.p, d_err.p));
     if (n_dir) KG_LAUNCH(ctx, low_words_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, nsorted, n_dir, nbr.p);
     uint32_t h_err = 0;
     int32_t h_max = 0;

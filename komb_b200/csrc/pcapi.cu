@@ -62,6 +62,33 @@ int kombgpu_dist_build_pairs_dev(kombgpu_comm *c, const uint32_t *u, const uint3
     return dist_build_common(c, u, v, n_pairs, n_global, false, out);
 }
 
+// host-pointer forms: the rank's share is uploaded first (what a host without CUDA headers calls, e.g. komb2)
+static int dist_build_host(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t count, uint32_t n_global, bool from_hits,
+                           kombgpu_dist_graph **out) {
+    if (!c) return KOMBGPU_EINVAL;
+    kombgpu_ctx *ctx = c->ctx;
+    if (!out || (count && (!a || !b))) return ctx_fail(ctx, KOMBGPU_EINVAL, "null argument");
+    KG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> da, db;
+    KG_ALLOC(ctx, da, count);
+    KG_ALLOC(ctx, db, count);
+    if (count) {
+        KG_CUDA(ctx, cudaMemcpyAsync(da.p, a, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        KG_CUDA(ctx, cudaMemcpyAsync(db.p, b, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return dist_build_common(c, da.p, db.p, count, n_global, from_hits, out);
+}
+
+int kombgpu_dist_build_hits(kombgpu_comm *c, const uint32_t *read_key, const uint32_t *unitig, uint64_t n_hits, uint32_t n_global,
+                            kombgpu_dist_graph **out) {
+    return dist_build_host(c, read_key, unitig, n_hits, n_global, true, out);
+}
+
+int kombgpu_dist_build_pairs(kombgpu_comm *c, const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t n_global,
+                             kombgpu_dist_graph **out) {
+    return dist_build_host(c, u, v, n_pairs, n_global, false, out);
+}
+
 int kombgpu_dist_coreness(kombgpu_dist_graph *g) {
     if (!g) return KOMBGPU_EINVAL;
     KG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));

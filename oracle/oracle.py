@@ -174,6 +174,53 @@ def densest_core(core: np.ndarray, edges: np.ndarray) -> dict:
     return best
 
 
+def max_core_truss(n: int, edges: np.ndarray, core: np.ndarray) -> dict:
+    """Kgraph::runTruss (src/graph.cpp:486-563) restated, for SMALL graphs (pure Python): the induced subgraph of the
+    vertices of maximal coreness (:470-476, :502), igraph_trussness of its edges (:508; the largest k such that the edge
+    lies in a k-truss, i.e. closes >= k - 2 triangles inside it; 2 without triangles) by the textbook support peel,
+    and the vertices on edges of maximal trussness (:519-533).  Returns edges as (u, v) original ids, canonical order."""
+    kmax = int(core.max()) if n else 0
+    inside = core == kmax
+    eu, ev = unpack_edges(edges)
+    keep = inside[eu] & inside[ev] if edges.size else np.zeros(0, bool)
+    su, sv = eu[keep].tolist(), ev[keep].tolist()
+    adj = {}
+    for a, b in zip(su, sv):
+        adj.setdefault(a, set()).add(b)
+        adj.setdefault(b, set()).add(a)
+    sup = {(a, b): len(adj[a] & adj[b]) for a, b in zip(su, sv)}
+    truss = {}
+    k = 2
+    alive = dict(sup)
+    while alive:
+        # peel every edge whose support is below what a (k + 1)-truss needs; what is peeled here has trussness k
+        queue = [e for e, s in alive.items() if s <= k - 2]
+        if not queue:
+            k += 1
+            continue
+        while queue:
+            e = queue.pop()
+            if e not in alive:
+                continue
+            a, b = e
+            del alive[e]
+            truss[e] = k
+            for w in adj[a] & adj[b]:
+                for f in ((min(a, w), max(a, w)), (min(b, w), max(b, w))):
+                    if f in alive:
+                        alive[f] -= 1
+                        if alive[f] <= k - 2:
+                            queue.append(f)
+            adj[a].discard(b)
+            adj[b].discard(a)
+    tr = np.array([truss[(a, b)] for a, b in zip(su, sv)], dtype=np.int32)
+    tmax = int(tr.max()) if tr.size else 0
+    verts = sorted({x for (a, b), t in truss.items() if t == tmax for x in (a, b)})
+    return {"n_core_vertices": int(inside.sum()), "n_core_edges": len(su), "max_trussness": tmax,
+            "u": np.array(su, np.uint32), "v": np.array(sv, np.uint32), "trussness": tr,
+            "truss_vertices": np.array(verts, np.uint32)}
+
+
 def unpack_edges(packed: np.ndarray):
     return (packed >> np.uint64(32)).astype(np.uint32), (packed & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 

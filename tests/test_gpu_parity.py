@@ -446,6 +446,44 @@ def test_two_contexts_in_one_process(oracle_mod):
             c.close()
 
 
+def test_max_core_truss(ctx, oracle_mod):
+    """kombgpu_graph_max_core_truss (reference Kgraph::runTruss, row N3) against the restatement in the oracle: the
+    induced subgraph of the maximal core, the trussness of every edge, the unitigs of the maximal truss; plus known
+    answers (K_7: every edge has trussness 7; a triangle-free core: trussness 2)."""
+    import komb_b200
+    cases = [synth.rmat_edges(11, 30000, n_vertices=1200, seed=2), synth.rmat_edges(14, 200000, n_vertices=9000, seed=5)]
+    m1, m2 = synth.metagenome_hits(3000, 9000, seed=3)
+    for i, (u, v) in enumerate(cases):
+        n = 1200 if i == 0 else 9000
+        edges = oracle_mod.simplify(u, v)
+        _, core = oracle_mod.coreness(n, edges)
+        exp = oracle_mod.max_core_truss(n, edges, core)
+        with ctx.graph_from_edges(u, v, n) as g:
+            with pytest.raises(komb_b200.KombGpuError):
+                g.max_core_truss()                       # needs the coreness first
+            g.coreness()
+            got = g.max_core_truss()
+        for key in ("n_core_vertices", "n_core_edges", "max_trussness"):
+            assert got[key] == exp[key], key
+        for key in ("u", "v", "trussness", "truss_vertices"):
+            assert np.array_equal(got[key], exp[key]), key
+    iu, iv = np.triu_indices(7, k=1)
+    with ctx.graph_from_edges(iu.astype(np.uint32) + 3, iv.astype(np.uint32) + 3, 12) as g:      # K_7 on ids 3..9
+        g.coreness()
+        got = g.max_core_truss()
+        assert (got["n_core_vertices"], got["n_core_edges"], got["max_trussness"]) == (7, 21, 7)
+        assert got["trussness"].tolist() == [7] * 21 and got["truss_vertices"].tolist() == list(range(3, 10))
+    ring = np.arange(8, dtype=np.uint32)
+    with ctx.graph_from_edges(ring, (ring + 1) % 8, 8) as g:                                      # C_8: no triangles
+        g.coreness()
+        got = g.max_core_truss()
+        assert got["max_trussness"] == 2 and got["trussness"].tolist() == [2] * 8 and got["truss_vertices"].tolist() == list(range(8))
+    with ctx.graph_from_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 5) as g:            # no edges
+        g.coreness()
+        got = g.max_core_truss()
+        assert (got["n_core_vertices"], got["n_core_edges"], got["max_trussness"]) == (5, 0, 0)
+
+
 def komb_b200_key_exact():
     import komb_b200
     return komb_b200.KEY_EXACT64

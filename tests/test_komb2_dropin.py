@@ -61,3 +61,26 @@ def test_komb2_exact64_key_mode(tmp_path, oracle_mod):
     exp = oracle_mod.komb2_expected(sam1, sam2, key_mode=oracle_mod.KEY_EXACT64)
     for nm, s in exp["score"].items():
         assert abs(got["score"][nm] - s) <= 5.0e-7 + 1e-12
+
+
+def _device_list():
+    """Distinct GPUs when the box has them, else every rank on device 0 (the library's emulation of several ranks on
+    one device: the same partitioned path, host-side exchanges)."""
+    import torch
+    n = torch.cuda.device_count()
+    return ",".join(str(d) for d in range(min(n, 4))) if n >= 2 else "0,0,0"
+
+
+@pytest.mark.parametrize("name", ["mid_s2", "quickstart_s1", "wide_s4"])
+def test_komb2_multi_gpu_outputs_match_reference(tmp_path, oracle_mod, name):
+    """KOMB_GPU_DEVICES=...: the C++ host drives one rank per device (threads, peer-memory path, no torch, no NCCL);
+    the three output files are the ones the reference writes."""
+    sam1, sam2, exp = load_komb2_case(name)
+    got, stdout = oracle_mod.run_komb2(KOMB2, sam1, sam2, tmp_path, threads=4, extra_env={"KOMB_GPU_DEVICES": _device_list()})
+    assert got["edges"] == exp["edges"]
+    assert got["kcore"] == exp["kcore"]
+    for nm, txt in exp["score_text"].items():
+        assert got["score_text"][nm] == txt or abs(float(got["score_text"][nm]) - float(txt)) <= 1.0000001e-6
+    for line in exp["stdout_info"]:
+        if not line.startswith("Max CoreA"):
+            assert line in stdout

@@ -131,3 +131,32 @@ def test_product_code_never_touches_the_oracle():
                 if pat.search(f.read_text(errors="ignore")):
                     offenders.append(str(f.relative_to(root)))
     assert offenders == [], offenders
+
+
+def test_truss_restatement_against_networkx(oracle_mod):
+    """oracle.max_core_truss (the restated Kgraph::runTruss) against networkx: k_core for the maximal core, k_truss
+    for the trussness of every edge."""
+    import networkx as nx
+    from komb_b200 import synth
+    for seed, n, m in [(1, 300, 6000), (2, 1200, 30000)]:
+        u, v = synth.rmat_edges(11, m, n_vertices=n, seed=seed)
+        edges = oracle_mod.simplify(u, v)
+        deg, core = oracle_mod.coreness(n, edges)
+        got = oracle_mod.max_core_truss(n, edges, core)
+        eu, ev = oracle_mod.unpack_edges(edges)
+        g = nx.Graph(); g.add_nodes_from(range(n)); g.add_edges_from(zip(eu.tolist(), ev.tolist()))
+        sub = nx.k_core(g)                                   # the maximal core
+        assert sub.number_of_nodes() == got["n_core_vertices"] and sub.number_of_edges() == got["n_core_edges"]
+        exp = {}
+        k = 2
+        while True:
+            t = nx.k_truss(sub, k)
+            if t.number_of_edges() == 0:
+                break
+            for a, b in t.edges():
+                exp[(min(a, b), max(a, b))] = k
+            k += 1
+        assert {(int(a), int(b)): int(t) for a, b, t in zip(got["u"], got["v"], got["trussness"])} == exp
+        assert got["max_trussness"] == k - 1
+        top = nx.k_truss(sub, k - 1)
+        assert sorted(x for x in top.nodes() if top.degree(x) > 0) == got["truss_vertices"].tolist()
