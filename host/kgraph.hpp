@@ -20,6 +20,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <future>
 #include <iostream>
 #include <memory>
@@ -122,6 +123,9 @@ class Kgraph {
     uint64_t _readlength;
     kombgpu_ctx *_ctx = nullptr;
     kombgpu_graph *_graph = nullptr;
+    kombgpu_hits *_hits = nullptr;       // device-resident hits when the SAM text is tokenised on the GPU
+    bool _gpu_tokenise = true;           // KOMB_TOKENIZE=host keeps the host tokeniser (always used with several GPUs)
+    std::vector<const MappedFile *> _sam_files;
     int _key_mode = KOMBGPU_KEY_REF32;
     int _device = 0;
     std::future<int> _ctx_ready;
@@ -164,6 +168,8 @@ class Kgraph {
    public:
     Kgraph(uint32_t threads, uint64_t readlength, int device, int key_mode, std::vector<int> devices = {})
         : _threads(threads ? threads : 1), _readlength(readlength), _key_mode(key_mode), _device(device), _devices(std::move(devices)) {
+        const char *tok_env = getenv("KOMB_TOKENIZE");
+        _gpu_tokenise = !multi() && !(tok_env && strcmp(tok_env, "host") == 0);
         if (multi()) { timing_mark("start"); return; }   // every rank's thread creates its own context (runMulti)
         // Creating the CUDA context costs seconds on a box without the persistence daemon (1.9 - 4.1 s measured on
         // the B200 boxes, against 0.75 s for everything else on a 2.5 M-hit SAM pair): do it on a helper thread
@@ -180,6 +186,7 @@ class Kgraph {
         if (_ctx_ready.valid()) _ctx_ready.wait();
         _efp.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();  // pinned buffers go before the context
         if (_graph) kombgpu_graph_destroy(_graph);
+        if (_hits) kombgpu_hits_destroy(_hits);
         if (_ctx) kombgpu_ctx_destroy(_ctx);
     }
 
@@ -197,6 +204,7 @@ class Kgraph {
     // Tokenise one SAM file; the mapped file must outlive `hits` (spans point into it).
     void readSAM(const std::string &samfile, MappedFile &file, HitTable &hits, bool /*fulgor: ignored like the reference*/) {
         if (!file.open(samfile)) fileNotFoundError(samfile);
+        if (_gpu_tokenise) { _sam_files.push_back(&file); return; }   // the bytes go to the device as they are (getEdgeInfo)
         try {
             tokenise_sam(file, (int)_threads, hits.tokens, samfile);
         } catch (const std::exception &e) {
@@ -209,6 +217,7 @@ class Kgraph {
     // Both mates are in `hits.tokens` now: intern read keys and unitig names.  The union of the two
     // mates' unitig sets per read (reference getEdgeInfo) needs no host work: equal keys get equal ids.
     void getEdgeInfo(HitTable &hits) {
+        if (_gpu_tokenise) { tokeniseOnDevice(hits); return; }
         timing_mark("tokenise SAMs");
         const size_t h = hits.tokens.keys.size();
         // ordered: ids follow first appearance, so the two mate files arrive as (at most) two runs of non-decreasing
@@ -236,6 +245,32 @@ class Kgraph {
 #pragma omp parallel for num_threads(_threads) schedule(static)
         for (size_t i = 0; i < h; ++i) hits.unitig[i] = vid[names.ids[n_sq + i]];
         timing_mark("intern keys + names");
+    }
+
+    // readSAM's tokeniser and the interning of read keys and unitig names, on the device (kombgpu_sam_parse): the host
+    // keeps only the unitig names, as spans of the mapped files.
+    void tokeniseOnDevice(HitTable &hits) {
+        timing_mark("map SAMs");
+        waitForDevice();
+        std::vector<const char *> texts;
+        std::vector<uint64_t> sizes;
+        for (const MappedFile *f : _sam_files) { texts.push_back(f->data); sizes.push_back(f->size); }
+        int rc = kombgpu_sam_parse(_ctx, texts.data(), sizes.data(), (int)texts.size(), &_hits);
+        if (rc == KOMBGPU_EINVAL) {   // malformed input: the host tokeniser's message and exit code
+            std::cerr << kombgpu_last_error(_ctx) << std::endl;
+            exit(EXIT_FAILURE);
+        }
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_sam_parse", rc);
+        uint32_t n = 0;
+        kombgpu_hits_counts(_hits, nullptr, nullptr, &n, nullptr);
+        std::vector<uint32_t> file(n), len(n);
+        std::vector<uint64_t> off(n);
+        rc = kombgpu_hits_names(_hits, file.data(), off.data(), len.data());
+        if (rc != KOMBGPU_OK) gpuError("kombgpu_hits_names", rc);
+        hits.names.resize(n);
+#pragma omp parallel for num_threads(_threads) schedule(static)
+        for (size_t i = 0; i < (size_t)n; ++i) hits.names[i].assign(_sam_files[file[i]]->data + off[i], len[i]);
+        timing_mark("tokenise + intern on the device");
     }
 
     // The whole device phase over several GPUs: hits split by read range (a read's hits stay together), one host
@@ -325,9 +360,10 @@ class Kgraph {
     void generateGraph(HitTable &hits) {
         if (multi()) { runMulti(hits); return; }
         waitForDevice();
-        int rc = kombgpu_build_graph(_ctx, hits.read_key.data(), hits.unitig.data(), hits.read_key.size(),
-                                     (uint32_t)hits.names.size(), &_graph);
-        if (rc != KOMBGPU_OK) gpuError("kombgpu_build_graph", rc);
+        int rc = _hits ? kombgpu_build_graph_hits(_hits, &_graph)
+                       : kombgpu_build_graph(_ctx, hits.read_key.data(), hits.unitig.data(), hits.read_key.size(),
+                                             (uint32_t)hits.names.size(), &_graph);
+        if (rc != KOMBGPU_OK) gpuError(_hits ? "kombgpu_build_graph_hits" : "kombgpu_build_graph", rc);
         timing_mark("kombgpu_build_graph");
     }
 

@@ -151,6 +151,33 @@ int kombgpu_graph_edge_multiplicity(const kombgpu_graph *g, uint32_t *mult);
 /* CSR of the symmetric graph: row_ptr[n+1], col[2E], every row ascending. */
 int kombgpu_graph_csr(const kombgpu_graph *g, uint64_t *row_ptr, uint32_t *col);
 
+/* ---- SAM text -> hits on the device ------------------------------------------
+ *
+ * The tokenising half of Kgraph::readSAM (src/graph.cpp:197-239, at -t 1: '@' lines skipped, tokens 0 and 2 under
+ * strtok("\t") rules, RNAME "*" skipped, read key = QNAME.substr(1, QNAME.find('/')), an unterminated final line
+ * is not processed) and the merge + vid assignment that follows it (src/graph.cpp:242-256), for a host that
+ * hands over the raw bytes of its SAM files instead of tokenising them itself.  `texts[f]` / `sizes[f]` are the
+ * bytes of input f (host pointers; mate 1 first).  Numbering is deterministic, unlike the reference's (quirk Q4):
+ * read ids follow first appearance; unitig ids follow @SQ header order, then first appearance, over unitigs with
+ * at least one hit.  Strings are matched by their bytes, never by hash alone.  Empty lines and lines with fewer
+ * than three tokens (undefined behaviour in the reference) fail with KOMBGPU_EINVAL.  The hits stay on the
+ * device: kombgpu_build_graph_hits builds the graph from them without a host round trip. */
+typedef struct kombgpu_hits kombgpu_hits;
+int kombgpu_sam_parse(kombgpu_ctx *ctx, const char *const *texts, const uint64_t *sizes, int n_files, kombgpu_hits **out);
+void kombgpu_hits_destroy(kombgpu_hits *hits);
+/* hits, distinct read keys, unitigs with a hit (= vertices), terminated lines seen; any pointer may be NULL */
+int kombgpu_hits_counts(const kombgpu_hits *hits, uint64_t *n_hits, uint32_t *n_reads, uint32_t *n_unitigs, uint64_t *n_lines);
+/* Name of every vertex as a span of the inputs: bytes [offset[v], offset[v] + len[v]) of input file[v]
+ * (n_unitigs entries each; `file` may be NULL).  The host keeps the strings, the device keeps the ids. */
+int kombgpu_hits_names(const kombgpu_hits *hits, uint32_t *file, uint64_t *offset, uint32_t *len);
+/* The integer hits in file order (n_hits entries each; either pointer may be NULL). */
+int kombgpu_hits_download(const kombgpu_hits *hits, uint32_t *read_key, uint32_t *unitig);
+int kombgpu_hits_device_arrays(const kombgpu_hits *hits, const uint32_t **read_key_dev, const uint32_t **unitig_dev);
+/* CUDA-event times of the upload and of the parse + interning kernels, kernels launched, hash seeds tried */
+int kombgpu_hits_timing(const kombgpu_hits *hits, float *ms_upload, float *ms_parse, uint64_t *kernel_launches, int *hash_rounds);
+/* kombgpu_build_graph_dev on the device-resident hits */
+int kombgpu_build_graph_hits(const kombgpu_hits *hits, kombgpu_graph **out);
+
 /* ---- stage 2: degree + coreness ------------------------------------------- */
 
 /* igraph_degree(ALL, NO_LOOPS) (src/graph.cpp:462): degree[n]. */

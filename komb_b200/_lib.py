@@ -94,6 +94,15 @@ SIGNATURES = {
     "kombgpu_graph_results": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kombgpu_graph_stats": (c_int, [c_void_p, POINTER(Stats)]),
     "kombgpu_graph_device_arrays": (c_int, [c_void_p] + [POINTER(c_void_p)] * 6),
+    # SAM text -> hits on the device
+    "kombgpu_sam_parse": (c_int, [c_void_p, POINTER(c_char_p), POINTER(c_uint64), c_int, POINTER(c_void_p)]),
+    "kombgpu_hits_destroy": (None, [c_void_p]),
+    "kombgpu_hits_counts": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint64)]),
+    "kombgpu_hits_names": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kombgpu_hits_download": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kombgpu_hits_device_arrays": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    "kombgpu_hits_timing": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_uint64), POINTER(c_int)]),
+    "kombgpu_build_graph_hits": (c_int, [c_void_p, POINTER(c_void_p)]),
     # multi-GPU partition interface
     "kombgpu_local_edges_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_edgeset_from_pairs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),

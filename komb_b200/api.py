@@ -165,6 +165,17 @@ class Context:
         r["u"], r["v"] = bu[:m], bv[:m]
         return graph, r
 
+    def sam_parse(self, texts) -> "Hits":
+        """SAM bytes of the mate files (mate 1 first) -> integer hits on the device (kombgpu_sam_parse): the GPU
+        form of Kgraph::readSAM's tokeniser + interner (src/graph.cpp:197-256)."""
+        texts = [bytes(t) for t in texts]
+        n = len(texts)
+        arr = (ctypes.c_char_p * max(n, 1))(*texts)
+        sizes = (c_uint64 * max(n, 1))(*[len(t) for t in texts])
+        h = c_void_p()
+        self._check(self._lib.kombgpu_sam_parse(self._h, arr, sizes, n, byref(h)))
+        return Hits(self, h, texts)
+
     def graph_from_edges(self, u, v, n_vertices: int) -> "Graph":
         return self._pair_call(self._lib.kombgpu_graph_from_edges, self._lib.kombgpu_graph_from_edges_dev,
                                u, v, int(n_vertices))
@@ -184,6 +195,58 @@ class Context:
         score = np.empty(c.shape[0], dtype=np.float64)
         self._check(self._lib.kombgpu_corea(self._h, _ptr(c), _ptr(d), c.shape[0], int(key_mode), _ptr(score)))
         return score
+
+
+class Hits:
+    """Device-resident tokenised hits of a set of SAM files (kombgpu_hits)."""
+
+    def __init__(self, ctx: Context, handle: c_void_p, texts):
+        self._ctx, self._lib, self._h, self._texts = ctx, ctx._lib, handle, texts
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kombgpu_hits_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def counts(self) -> dict:
+        nh, nr, nu, nl = c_uint64(), c_uint32(), c_uint32(), c_uint64()
+        self._ctx._check(self._lib.kombgpu_hits_counts(self._h, byref(nh), byref(nr), byref(nu), byref(nl)))
+        return {"n_hits": nh.value, "n_reads": nr.value, "n_unitigs": nu.value, "n_lines": nl.value}
+
+    def names(self) -> list[bytes]:
+        """Unitig name of every vertex, cut out of the input bytes with the spans the device reports."""
+        n = self.counts()["n_unitigs"]
+        f, off, ln = np.empty(n, np.uint32), np.empty(n, np.uint64), np.empty(n, np.uint32)
+        self._ctx._check(self._lib.kombgpu_hits_names(self._h, _ptr(f), _ptr(off), _ptr(ln)))
+        return [self._texts[int(f[i])][int(off[i]):int(off[i]) + int(ln[i])] for i in range(n)]
+
+    def download(self) -> tuple[np.ndarray, np.ndarray]:
+        n = self.counts()["n_hits"]
+        rk, ut = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        self._ctx._check(self._lib.kombgpu_hits_download(self._h, _ptr(rk), _ptr(ut)))
+        return rk, ut
+
+    def timing(self) -> dict:
+        a, b, l, r = ctypes.c_float(), ctypes.c_float(), c_uint64(), ctypes.c_int()
+        self._ctx._check(self._lib.kombgpu_hits_timing(self._h, byref(a), byref(b), byref(l), byref(r)))
+        return {"ms_upload": a.value, "ms_parse": b.value, "kernel_launches": l.value, "hash_rounds": r.value}
+
+    def build_graph(self) -> "Graph":
+        g = c_void_p()
+        self._ctx._check(self._lib.kombgpu_build_graph_hits(self._h, byref(g)))
+        return Graph(self._ctx, g, self)
 
 
 class Graph:

@@ -16,10 +16,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", [n for n in komb2_case_names() if not n.endswith("_t4")])
-@pytest.mark.parametrize("threads", [1, 5])
-def test_komb2_outputs_match_reference(tmp_path, oracle_mod, name, threads):
+@pytest.mark.parametrize("threads,tokenise", [(1, "gpu"), (5, "gpu"), (3, "host")])
+def test_komb2_outputs_match_reference(tmp_path, oracle_mod, name, threads, tokenise):
+    """tokenise: SAM text parsed and interned on the device (kombgpu_sam_parse, the default) or by the host tokeniser."""
     sam1, sam2, exp = load_komb2_case(name)
-    got, stdout = oracle_mod.run_komb2(KOMB2, sam1, sam2, tmp_path, threads=threads)
+    got, stdout = oracle_mod.run_komb2(KOMB2, sam1, sam2, tmp_path, threads=threads, extra_env={"KOMB_TOKENIZE": tokenise})
     assert got["edges"] == exp["edges"]
     assert got["kcore"] == exp["kcore"]
     assert set(got["score_text"]) == set(exp["score_text"])
@@ -53,6 +54,14 @@ def test_komb2_error_behaviour(tmp_path):
     cp = subprocess.run([str(KOMB2), "-i", str(tmp_path / "missing.sam"), "-j", "b", "-u", "c", "-o", str(tmp_path)],
                         capture_output=True, text=True)
     assert cp.returncode == 1 and "could not be opened" in cp.stderr
+    # malformed SAM text is rejected with a message, by the device tokeniser and by the host one
+    (tmp_path / "bad.sam").write_bytes(b"r1/1\t0\tu1\nonlyonefield\n")
+    (tmp_path / "ok.sam").write_bytes(b"r1/2\t0\tu2\n")
+    (tmp_path / "u.fa").write_text(">u1\nACGT\n")
+    for mode in ("gpu", "host"):
+        cp = subprocess.run([str(KOMB2), "-i", str(tmp_path / "bad.sam"), "-j", str(tmp_path / "ok.sam"), "-u", str(tmp_path / "u.fa"),
+                             "-o", str(tmp_path)], capture_output=True, text=True, env={**__import__("os").environ, "KOMB_TOKENIZE": mode})
+        assert cp.returncode == 1 and "malformed SAM" in cp.stderr and "fewer than 3" in cp.stderr
 
 
 def test_komb2_exact64_key_mode(tmp_path, oracle_mod):
