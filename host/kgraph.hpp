@@ -125,6 +125,9 @@ class Kgraph {
     kombgpu_graph *_graph = nullptr;
     kombgpu_hits *_hits = nullptr;       // device-resident hits when the SAM text is tokenised on the GPU
     bool _gpu_tokenise = true;           // KOMB_TOKENIZE=host keeps the host tokeniser (always used with several GPUs)
+    bool _device_output = true;          // KOMB_OUTPUT=host formats the three files on the host (always without device hits)
+    std::unique_ptr<PinnedArray<char>> _text[3];   // the files' bytes, formatted on the device
+    uint64_t _text_bytes[3] = {0, 0, 0};
     std::vector<const MappedFile *> _sam_files;
     int _key_mode = KOMBGPU_KEY_REF32;
     int _device = 0;
@@ -170,6 +173,8 @@ class Kgraph {
         : _threads(threads ? threads : 1), _readlength(readlength), _key_mode(key_mode), _device(device), _devices(std::move(devices)) {
         const char *tok_env = getenv("KOMB_TOKENIZE");
         _gpu_tokenise = !multi() && !(tok_env && strcmp(tok_env, "host") == 0);
+        const char *out_env = getenv("KOMB_OUTPUT");
+        _device_output = _gpu_tokenise && !(out_env && strcmp(out_env, "host") == 0);
         if (multi()) { timing_mark("start"); return; }   // every rank's thread creates its own context (runMulti)
         // Creating the CUDA context costs seconds on a box without the persistence daemon (1.9 - 4.1 s measured on
         // the B200 boxes, against 0.75 s for everything else on a 2.5 M-hit SAM pair): do it on a helper thread
@@ -185,6 +190,7 @@ class Kgraph {
     ~Kgraph() {
         if (_ctx_ready.valid()) _ctx_ready.wait();
         _efp.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();  // pinned buffers go before the context
+        for (auto &t : _text) t.reset();
         if (_graph) kombgpu_graph_destroy(_graph);
         if (_hits) kombgpu_hits_destroy(_hits);
         if (_ctx) kombgpu_ctx_destroy(_ctx);
@@ -405,6 +411,39 @@ class Kgraph {
             return;
         }
         kombgpu_graph_counts(_graph, &n, &m);
+        if (_device_output) {
+            // the files are formatted on the device (kombgpu_graph_format): the edge list first, its download runs on the
+            // copy stream under the peel and CORE-A; the host issues one write per file
+            auto fetch = [&](int which, bool async) {
+                int rc = kombgpu_graph_format(_graph, which, _hits, &_text_bytes[which]);
+                if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_format", rc);
+                _text[which].reset(new PinnedArray<char>(_ctx, _text_bytes[which]));
+                rc = kombgpu_graph_format_fetch(_graph, which, _text[which]->data(), async ? 1 : 0);
+                if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_format_fetch", rc);
+            };
+            fetch(KOMBGPU_FILE_EDGELIST, true);
+            int rc = kombgpu_graph_analyse(_graph, _key_mode);
+            if (rc != KOMBGPU_OK) gpuError("kombgpu_graph_analyse", rc);
+            fetch(KOMBGPU_FILE_KCORE, true);
+            fetch(KOMBGPU_FILE_COREA, true);
+            if ((rc = kombgpu_graph_format_wait(_graph)) != KOMBGPU_OK) gpuError("kombgpu_graph_format_wait", rc);
+            timing_mark("format on the device + download");
+            if (_text_bytes[0] && fwrite(_text[0]->data(), 1, _text_bytes[0], ef) != _text_bytes[0]) fileNotFoundError(edgelist_file);
+            fclose(ef);
+            _text[0].reset();
+            timing_mark("write edgelist.txt");
+            fprintf(stdout, "\nTime elapsed for initializing igraph graph: %.3f s\n", seconds_since(begin_graph));
+            fprintf(stdout, "\nTime elapsed for simplifying graph: %.3f s\n", 0.0);
+            fprintf(stdout, "GraphInfo...\n\tNumber of vertices: %d\n", (int)n);
+            fprintf(stdout, "\tNumber of edges: %d\n", (int)m);
+            FILE *uf3 = fopen(inputUnitigs.c_str(), "r");
+            if (uf3 == nullptr) fileNotFoundError(inputUnitigs);
+            fclose(uf3);
+            auto begin_kcore3 = std::chrono::steady_clock::now();
+            runCore(dir, hits);
+            fprintf(stdout, "\nTime elapsed doing K-core decomposition: %.3f s\n", seconds_since(begin_kcore3));
+            return;
+        }
         // one call fetches everything the three output files need; the edge-list download (CSR form: offsets per
         // source + targets, half the bytes of two id arrays) overlaps the peel
         _efp.reset(new PinnedArray<uint64_t>(_ctx, (size_t)n + 1));
@@ -445,6 +484,15 @@ class Kgraph {
     void runCore(const std::string &dir, HitTable &hits) {
         const std::string kcore_file = dir + "/kcore.tsv";
         const uint32_t n = (uint32_t)hits.names.size();
+        if (_device_output && !multi()) {
+            FILE *kf = fopen(kcore_file.c_str(), "w+");
+            if (kf == nullptr) fileNotFoundError(kcore_file);
+            if (fwrite(_text[1]->data(), 1, _text_bytes[1], kf) != _text_bytes[1]) fileNotFoundError(kcore_file);
+            fclose(kf);
+            _text[1].reset();
+            timing_mark("write kcore.tsv");
+            return;
+        }
         // fetched by readEdgeList (one GPU) or runMulti (every rank's slice)
         std::vector<int32_t> deg_all, core_all;
         if (multi()) {
@@ -486,7 +534,7 @@ class Kgraph {
             kombgpu_graph_counts(_graph, &n, nullptr);
             kombgpu_graph_summary(_graph, &max_core, &max_score);
         }
-        const double *score = multi() ? score_all.data() : _score->data();  // fetched by readEdgeList / runMulti
+        const double *score = multi() ? score_all.data() : (_score ? _score->data() : nullptr);  // fetched by readEdgeList / runMulti
         const double dense_ratio = (double)(max_core / 2);  // integer division, like CombineCoreA.h:24
         fprintf(stdout, "Dense Ratio: %f\n", n ? dense_ratio : 0.0);
         if (weight) {
@@ -494,6 +542,9 @@ class Kgraph {
             const std::string anomaly_output = dir + "/CoreA_anomaly.txt";
             FILE *fp = fopen(anomaly_output.c_str(), "w+");
             if (fp == nullptr) fileNotFoundError(anomaly_output);
+            if (_device_output && !multi()) {
+                if (_text_bytes[2] && fwrite(_text[2]->data(), 1, _text_bytes[2], fp) != _text_bytes[2]) fileNotFoundError(anomaly_output);
+            } else
             write_rows(fp, n, 64, (int)_threads, [&](char *p, size_t i) {
                 p = put_u64(p, i); *p++ = '\t';
                 p += snprintf(p, 48, "%f\n", score[i]);
@@ -503,6 +554,7 @@ class Kgraph {
             timing_mark("write CoreA_anomaly.txt");
         }
         _efp.reset(); _ev.reset(); _deg.reset(); _core.reset(); _score.reset();
+        for (auto &t : _text) t.reset();
         _ranks.clear();
         if (_graph) kombgpu_graph_destroy(_graph);
         _graph = nullptr;

@@ -8,7 +8,10 @@
 //              KOMB_GPU_DEVICES=0,1,... (two or more ordinals: the graph is partitioned over these GPUs of the node,
 //              one host thread per GPU, peer-memory path of libkombgpu; same output files);
 //              KOMB_COREA_KEY=exact64 selects the overflow-free CORE-A key
-//              (default "ref32" reproduces the reference's int32 wrap, quirk Q5).
+//              (default "ref32" reproduces the reference's int32 wrap, quirk Q5);
+//              KOMB_TOKENIZE=host tokenises and interns the SAM text on the host (default with one GPU: on the device,
+//              kombgpu_sam_parse); KOMB_OUTPUT=host formats the three files on the host (default with device
+//              tokenisation: on the device, kombgpu_graph_format); KOMB_TIMING=1 prints wall-clock marks.
 #include <omp.h>
 
 #include <chrono>

@@ -204,6 +204,25 @@ int kombgpu_graph_corea(kombgpu_graph *g, int key_mode, double *score);
  * CORE-A score. */
 int kombgpu_graph_summary(const kombgpu_graph *g, int32_t *max_coreness, double *max_score);
 
+/* ---- output files formatted on the device ----------------------------------
+ *
+ * The bytes of the three files the reference writes with one fprintf per row: edgelist.txt "%d\t%d\n" per simple
+ * edge in canonical order (src/graph.cpp:423-426; quirk Q7), kcore.tsv "#VID\tName\tCoreness\tDegree\n" +
+ * "%d\t%s\t%d\t%d\n" per unitig (src/graph.cpp:467-475) and CoreA_anomaly.txt "%d\t%f\n" per unitig
+ * (src/CombineCoreA.h:36-39; "%f" as glibc prints it: six decimals of the exact binary value, ties to even).
+ * kombgpu_graph_format formats file `which` on the device and reports its size; kombgpu_graph_format_fetch copies
+ * it to the host -- with async != 0 on the copy stream, so that compute issued afterwards (the peel under the
+ * edge-list download) overlaps it; kombgpu_graph_format_wait ends the asynchronous copies.  KCORE needs the
+ * coreness and the kombgpu_hits the graph was built from (the names live in its copy of the SAM text); COREA
+ * needs the scores.  The host issues one write per file. */
+enum { KOMBGPU_FILE_EDGELIST = 0, KOMBGPU_FILE_KCORE = 1, KOMBGPU_FILE_COREA = 2 };
+int kombgpu_graph_format(kombgpu_graph *g, int which, const kombgpu_hits *names, uint64_t *bytes);
+int kombgpu_graph_format_fetch(kombgpu_graph *g, int which, char *dst, int async);
+int kombgpu_graph_format_wait(kombgpu_graph *g);
+/* CoreA_anomaly.txt from a host array of scores (finite, |score| < 2^43): *bytes = size of the text; it is
+ * copied to dst when it fits `capacity` (else KOMBGPU_EINVAL, *bytes still set). */
+int kombgpu_format_corea(kombgpu_ctx *ctx, const double *score, uint32_t n, char *dst, uint64_t capacity, uint64_t *bytes);
+
 /* ---- whole path + introspection --------------------------------------------- */
 
 /* build (already done) -> coreness -> CORE-A in one call, results left on the

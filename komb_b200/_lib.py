@@ -103,6 +103,11 @@ SIGNATURES = {
     "kombgpu_hits_device_arrays": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     "kombgpu_hits_timing": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_uint64), POINTER(c_int)]),
     "kombgpu_build_graph_hits": (c_int, [c_void_p, POINTER(c_void_p)]),
+    # output files formatted on the device
+    "kombgpu_graph_format": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_uint64)]),
+    "kombgpu_graph_format_fetch": (c_int, [c_void_p, c_int, c_void_p, c_int]),
+    "kombgpu_graph_format_wait": (c_int, [c_void_p]),
+    "kombgpu_format_corea": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, POINTER(c_uint64)]),
     # multi-GPU partition interface
     "kombgpu_local_edges_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "kombgpu_edgeset_from_pairs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),

@@ -187,6 +187,15 @@ class Context:
                                                          c_void_p(col.data_ptr() if col.numel() else 0), int(n_vertices), byref(g)))
         return Graph(self, g, (row_ptr, col))
 
+    def format_corea(self, score) -> bytes:
+        """CoreA_anomaly.txt ("%d\\t%f\\n" rows) from a host array of scores, formatted on the device."""
+        sc = _host(score, np.float64)
+        n = c_uint64()
+        cap = 40 * sc.shape[0] + 16
+        buf = ctypes.create_string_buffer(cap)
+        self._check(self._lib.kombgpu_format_corea(self._h, _ptr(sc), sc.shape[0], buf, cap, byref(n)))
+        return buf.raw[:n.value]
+
     def corea(self, coreness, degree, key_mode: int = KEY_REF32) -> np.ndarray:
         """CoreA::getAnomalyScore on host arrays."""
         c, d = _host(coreness, np.int32), _host(degree, np.int32)
@@ -372,6 +381,17 @@ class Graph:
 
     def analyse(self, key_mode: int = KEY_REF32):
         self._ctx._check(self._lib.kombgpu_graph_analyse(self._h, int(key_mode)))
+
+    FILE_EDGELIST, FILE_KCORE, FILE_COREA = 0, 1, 2
+
+    def format(self, which: int, hits: "Hits | None" = None) -> bytes:
+        """The bytes of edgelist.txt / kcore.tsv / CoreA_anomaly.txt, formatted on the device (kombgpu_graph_format);
+        kcore.tsv takes the unitig names from the Hits the graph was built from."""
+        n = c_uint64()
+        self._ctx._check(self._lib.kombgpu_graph_format(self._h, int(which), hits._h if hits is not None else None, byref(n)))
+        buf = ctypes.create_string_buffer(max(n.value, 1))
+        self._ctx._check(self._lib.kombgpu_graph_format_fetch(self._h, int(which), buf, 0))
+        return buf.raw[:n.value]
 
     def summary(self) -> tuple[int, float]:
         mc, ms = c_int32(), c_double()

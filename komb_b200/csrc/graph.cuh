@@ -28,6 +28,9 @@ struct kombgpu_graph {
     uint64_t *tr_edges = nullptr;      // [tr_m] induced edges, compact ids (a << 32 | b), canonical order
     int32_t *tr_truss = nullptr;       // [tr_m]
     uint32_t *tr_vertices = nullptr;   // [tr_n_vertices] original ids of the unitigs on edges of maximal trussness
+    // output files formatted on the device (format.cu): edgelist.txt, kcore.tsv, CoreA_anomaly.txt
+    char *text[3] = {nullptr, nullptr, nullptr};
+    uint64_t text_bytes[3] = {0, 0, 0};
 };
 
 namespace kg {
@@ -78,5 +81,6 @@ int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint
 
 void graph_release(kombgpu_graph *g);
 void truss_release(kombgpu_graph *g);   // truss.cu
+void format_release(kombgpu_graph *g);  // format.cu
 
 }  // namespace kg

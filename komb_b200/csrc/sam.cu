@@ -503,6 +503,15 @@ int sam_parse(kombgpu_ctx *ctx, const char *const *texts, const uint64_t *sizes,
 }
 
 }  // namespace
+
+// the unitig names as spans of the device copy of the text (format.cu writes kcore.tsv from them)
+int hits_name_spans(const kombgpu_hits *h, kombgpu_ctx **ctx, const unsigned char **text, const uint64_t **off, const uint32_t **len,
+                    uint32_t *n_unitigs) {
+    if (!h) return KOMBGPU_EINVAL;
+    *ctx = h->ctx; *text = h->text; *off = h->name_off; *len = h->name_len; *n_unitigs = h->n_unitigs;
+    return KOMBGPU_OK;
+}
+
 }  // namespace kg
 
 using namespace kg;

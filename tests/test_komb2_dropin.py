@@ -16,11 +16,13 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", [n for n in komb2_case_names() if not n.endswith("_t4")])
-@pytest.mark.parametrize("threads,tokenise", [(1, "gpu"), (5, "gpu"), (3, "host")])
-def test_komb2_outputs_match_reference(tmp_path, oracle_mod, name, threads, tokenise):
-    """tokenise: SAM text parsed and interned on the device (kombgpu_sam_parse, the default) or by the host tokeniser."""
+@pytest.mark.parametrize("threads,tokenise,output", [(1, "gpu", "gpu"), (5, "gpu", "host"), (3, "host", "host")])
+def test_komb2_outputs_match_reference(tmp_path, oracle_mod, name, threads, tokenise, output):
+    """tokenise: SAM text parsed and interned on the device (kombgpu_sam_parse, the default) or by the host tokeniser;
+    output: the three files formatted on the device (kombgpu_graph_format, the default) or by the host."""
     sam1, sam2, exp = load_komb2_case(name)
-    got, stdout = oracle_mod.run_komb2(KOMB2, sam1, sam2, tmp_path, threads=threads, extra_env={"KOMB_TOKENIZE": tokenise})
+    got, stdout = oracle_mod.run_komb2(KOMB2, sam1, sam2, tmp_path, threads=threads,
+                                       extra_env={"KOMB_TOKENIZE": tokenise, "KOMB_OUTPUT": output})
     assert got["edges"] == exp["edges"]
     assert got["kcore"] == exp["kcore"]
     assert set(got["score_text"]) == set(exp["score_text"])

@@ -126,3 +126,49 @@ def test_many_distinct_strings_and_long_names(ctx, oracle_mod):
                 lines.append(b"Rread%d/%d\t0\t%s\t1\t60" % (r, mate, unitig_names[int(rng.integers(0, n_unitigs))]))
     s1, s2 = b"\n".join(lines1) + b"\n", b"\n".join(lines2) + b"\n"
     check_against_restatement(oracle_mod, ctx, [s1, s2])
+
+
+# ---- output files formatted on the device (row N2) --------------------------------------------------------------
+
+def test_percent_f_matches_glibc(ctx):
+    """"%f" on the device = six decimals of the exact binary value, ties to even (Python's % formatting is the same rule)."""
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([
+        np.array([0.0, 1.0 / 128, 3.0 / 128, 0.5, 0.9999995, 0.99999949999, 1e-7, 4.9e-324, 2.5e-7, 5e-7, 1.5e-6, 22.180709777918249,
+                  123456.7890125, 8796093022207.5, 1e-300, 0.1, 0.2 + 0.1]),
+        rng.random(20000) * 25.0, rng.random(2000) * 1e-5, np.ldexp(rng.integers(1, 1 << 20, 2000).astype(np.float64), -rng.integers(1, 30, 2000)),
+    ])
+    got = ctx.format_corea(xs).decode().split("\n")
+    assert got[-1] == "" and len(got) == xs.shape[0] + 1
+    for i, x in enumerate(xs.tolist()):
+        assert got[i] == "%d\t%f" % (i, x), (i, x)
+    import komb_b200
+    for bad in (np.inf, np.nan, 2.0 ** 43):
+        with pytest.raises(komb_b200.KombGpuError):
+            ctx.format_corea(np.array([1.0, bad]))
+    assert ctx.format_corea(np.zeros(0)) == b""
+
+
+@pytest.mark.parametrize("name", ["mid_s2", "quickstart_s1", "wide_s4"])
+def test_device_formatted_files(ctx, name):
+    """The three files' bytes from the device = what the host would print row by row from the downloaded arrays."""
+    sam1, sam2, _ = load_komb2_case(name)
+    with ctx.sam_parse([sam1, sam2]) as hits:
+        names = hits.names()
+        with hits.build_graph() as g:
+            u, v = g.edges()
+            deg, core, score = g.degree(), g.coreness(), g.corea()
+            assert g.format(g.FILE_EDGELIST) == b"".join(b"%d\t%d\n" % (a, b) for a, b in zip(u.tolist(), v.tolist()))
+            exp_k = b"#VID\tName\tCoreness\tDegree\n" + b"".join(
+                b"%d\t%s\t%d\t%d\n" % (i, names[i], int(core[i]), int(deg[i])) for i in range(len(names)))
+            assert g.format(g.FILE_KCORE, hits) == exp_k
+            assert g.format(g.FILE_COREA) == b"".join(b"%d\t%f\n" % (i, float(s)) for i, s in enumerate(score))
+    # kcore.tsv needs the names (the hits the graph was built from); the other two files do not
+    import komb_b200
+    with ctx.build_graph(np.array([0, 0, 1, 1], np.uint32), np.array([0, 1, 1, 2], np.uint32), 3) as g2:
+        g2.coreness()
+        with pytest.raises(komb_b200.KombGpuError, match="names"):
+            g2.format(g2.FILE_KCORE)
+        with pytest.raises(komb_b200.KombGpuError, match="corea"):
+            g2.format(g2.FILE_COREA)
+        assert g2.format(g2.FILE_EDGELIST) == b"0\t1\n1\t2\n"
