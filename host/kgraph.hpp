@@ -269,6 +269,15 @@ class Kgraph {
         if (rc != KOMBGPU_OK) gpuError("kombgpu_sam_parse", rc);
         uint32_t n = 0;
         kombgpu_hits_counts(_hits, nullptr, nullptr, &n, nullptr);
+        if (getenv("KOMB_TIMING")) {
+            float up = 0.f, parse = 0.f;
+            uint64_t launches = 0;
+            kombgpu_hits_timing(_hits, &up, &parse, &launches, nullptr);
+            fprintf(stderr, "[komb2 timing]   device tokeniser: upload %.3f ms, parse + intern %.3f ms, %llu kernels\n", up, parse,
+                    (unsigned long long)launches);
+        }
+        timing_mark("kombgpu_sam_parse");
+        if (_device_output) return;   // kcore.tsv is formatted on the device from its copy of the text: no names on the host
         std::vector<uint32_t> file(n), len(n);
         std::vector<uint64_t> off(n);
         rc = kombgpu_hits_names(_hits, file.data(), off.data(), len.data());
@@ -276,7 +285,7 @@ class Kgraph {
         hits.names.resize(n);
 #pragma omp parallel for num_threads(_threads) schedule(static)
         for (size_t i = 0; i < (size_t)n; ++i) hits.names[i].assign(_sam_files[file[i]]->data + off[i], len[i]);
-        timing_mark("tokenise + intern on the device");
+        timing_mark("unitig names to the host");
     }
 
     // The whole device phase over several GPUs: hits split by read range (a read's hits stay together), one host

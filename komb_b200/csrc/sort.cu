@@ -10,7 +10,9 @@
 // What bounds a pass is instruction issue, not DRAM: ~130 thread-instructions per key, half of them the
 // ballot-per-digit-bit ranking (ncu: issue slots 50 % busy, ALU pipe 49 %, barrier stalls 44 % of samples, DRAM
 // 25 % of peak; profiles/r1/r1o_sweep_*).  MATCH.ANY ranks a key in one instruction but runs on the ADU pipe
-// and made every mix of the two slower (KOMBGPU_SORT_MATCH, measured 0/2/4/8 items).
+// and made every mix of the two slower (measured in round 1 with 0/2/4/8 items per thread; removed since).
+// Tile geometries measured in round 2 (33 M pair keys, 5 passes; profiles/r2/r2v_sort_geometries.log): 512 x 16 keys
+// 1.30 ms, 256 x 16 (4 CTAs/SM) 1.35, 256 x 16 (3) 1.85, 128 x 16 (8) 1.74, 256 x 8 (6) 1.61, 384 x 16 (2) 1.82.
 #include <cstdlib>
 
 #include "kombgpu_debug.h"
@@ -225,72 +227,61 @@ __global__ void __launch_bounds__(kRadix) radix_hist_scan_kernel(uint32_t *hist)
     h[threadIdx.x] = ex;
 }
 
-// tile geometry of the sweep kernel.  Measured on the 33 M-key shape: 512 x 16 keys 1.58 ms per 6-pass sort,
-// 512 x 8 1.70 ms, 256 x 8 1.82 ms: the per-digit phases (prefix over warps, look-back: 256 threads, the rest of
-// the CTA waits at a barrier) are amortised over more keys.
-constexpr int kSwThreads = 512;
-constexpr int kSwItems = 16;
-constexpr int kSwTile = kSwThreads * kSwItems;
-constexpr int kSwWarps = kSwThreads / 32;
-constexpr int kSwMinBlocks = 2;
-
-struct SweepSmem {
-    uint64_t keys[kSwTile];
-    uint32_t warp_cnt[kSwWarps][kRadix];
+// tile geometry of the sweep kernel: kThreads x kItems keys per CTA, kMinBlocks CTAs per SM.  Measured on the 33 M-key
+// shape (6-pass sort): 512 x 16 keys 1.58 ms, 512 x 8 1.70 ms, 256 x 8 1.82 ms: the per-digit phases (prefix over warps,
+// look-back) are amortised over more keys.  KOMBGPU_SORT_TILE selects a geometry for A/B runs.
+template <int kThreads, int kItems>
+struct SweepSmemT {
+    uint64_t keys[kThreads * kItems];
+    uint32_t warp_cnt[kThreads / 32][kRadix];
     uint32_t digit_local[kRadix];   // first slot of digit d inside the staged tile
     uint32_t digit_global[kRadix];  // global position of that slot minus digit_local
-    uint32_t scan_tmp[kRadix / 32 + 1];
+    uint32_t digit_total[kRadix];
     uint32_t tile;
 };
 
-// kBits: digit width known at compile time (8), or 0 = read it from `mask`.  kMatch: items per thread ranked with
-// MATCH.ANY instead of ballots.  MATCH is one instruction where the ballot way takes ~50, but it runs on the
-// slow ADU pipe; ranking a few of the 8 items with it spreads the work over both pipes.
-template <int kBits, int kMatch>
-__global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
+// kBits: digit width known at compile time (8), or 0 = read it from `mask`.
+template <int kBits, int kThreads, int kItems, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) radix_sweep_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
                                                                     uint64_t n, DigitSpec dg,
                                                                     const uint32_t *__restrict__ digit_base,  // exclusive global histogram of this pass
                                                                     uint32_t *status, uint32_t *tile_counter) {
+    constexpr int kTile = kThreads * kItems, kWarps = kThreads / 32;
     extern __shared__ __align__(16) unsigned char s_raw[];
-    SweepSmem &s = *reinterpret_cast<SweepSmem *>(s_raw);
+    SweepSmemT<kThreads, kItems> &s = *reinterpret_cast<SweepSmemT<kThreads, kItems> *>(s_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t mask = kBits ? (1u << kBits) - 1u : dg.mask;
     if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
-    for (int i = threadIdx.x; i < kSwWarps * kRadix; i += kSwThreads) (&s.warp_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&s.warp_cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
-    const uint64_t tile_base = (uint64_t)tile * kSwTile;
-    const uint32_t tile_count = (uint32_t)min((uint64_t)kSwTile, n - tile_base);
+    const uint64_t tile_base = (uint64_t)tile * kTile;
+    const uint32_t tile_count = (uint32_t)min((uint64_t)kTile, n - tile_base);
 
-    // warp-striped load: item j of lane l is tile element warp*256 + j*32 + l, so (warp, j, lane) order is memory
+    // warp-striped load: item j of lane l is tile element warp*32*kItems + j*32 + l, so (warp, j, lane) order is memory
     // order and the sort stays stable
-    uint64_t key[kSwItems];
-    uint16_t rank[kSwItems];
-    const uint32_t warp_base = warp * (32 * kSwItems);
+    uint64_t key[kItems];
+    uint16_t rank[kItems];
+    const uint32_t warp_base = warp * (32 * kItems);
 #pragma unroll
-    for (int j = 0; j < kSwItems; ++j) {
+    for (int j = 0; j < kItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         key[j] = e < tile_count ? in[tile_base + e] : 0;
     }
-    // rank inside the warp: lanes with the same digit are found with one ballot per digit bit (or one MATCH); the
-    // group's leader takes the digit's running count with a shared-memory atomic (issued in j order: stable)
+    // rank inside the warp: lanes with the same digit are found with one ballot per digit bit; the group's leader takes
+    // the digit's running count with a shared-memory atomic (issued in j order: stable)
 #pragma unroll
-    for (int j = 0; j < kSwItems; ++j) {
+    for (int j = 0; j < kItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         const bool valid = e < tile_count;
         const uint32_t d = valid ? dg(key[j]) : 0u;
-        uint32_t same;
-        if (j < kMatch) {
-            same = __match_any_sync(kFullMask, valid ? d : 0xffffffffu);   // invalid lanes (tail of the last tile) group apart
-        } else {
-            same = __ballot_sync(kFullMask, valid);
+        uint32_t same = __ballot_sync(kFullMask, valid);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (kBits ? (b >= kBits) : ((mask >> b) == 0)) break;  // uniform: narrower digits need fewer ballots
-                const uint32_t bit = (d >> b) & 1u;
-                const uint32_t vote = __ballot_sync(kFullMask, bit);
-                same &= vote ^ (bit - 1u);   // lanes whose bit equals mine
-            }
+        for (int b = 0; b < 8; ++b) {
+            if (kBits ? (b >= kBits) : ((mask >> b) == 0)) break;  // uniform: narrower digits need fewer ballots
+            const uint32_t bit = (d >> b) & 1u;
+            const uint32_t vote = __ballot_sync(kFullMask, bit);
+            same &= vote ^ (bit - 1u);   // lanes whose bit equals mine
         }
         const uint32_t lead = valid ? (uint32_t)__ffs(same) - 1u : lane;
         uint32_t base = 0;
@@ -299,52 +290,49 @@ __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(c
     }
     __syncthreads();
 
-    // per digit: exclusive prefix over warps; publish the tile's count; start the look-back
-    uint32_t digit_total = 0;
-    const bool digit_thread = threadIdx.x < kRadix;
-    if (digit_thread) {
-        for (int w = 0; w < kSwWarps; ++w) {
-            const uint32_t c = s.warp_cnt[w][threadIdx.x];
-            s.warp_cnt[w][threadIdx.x] = digit_total;
-            digit_total += c;
+    // per digit: exclusive prefix over warps; publish the tile's count (the look-back starts from it)
+    for (uint32_t d = threadIdx.x; d < (uint32_t)kRadix; d += kThreads) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = s.warp_cnt[w][d];
+            s.warp_cnt[w][d] = total;
+            total += c;
         }
-        if (threadIdx.x <= mask) {
-            uint32_t *mine = status + (size_t)tile * kRadix + threadIdx.x;
-            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(mine), "r"((tile == 0 ? kFlagPrefix : kFlagAgg) | digit_total) : "memory");
+        s.digit_total[d] = total;
+        if (d <= mask) {
+            uint32_t *mine = status + (size_t)tile * kRadix + d;
+            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(mine), "r"((tile == 0 ? kFlagPrefix : kFlagAgg) | total) : "memory");
         }
     }
-    {
-        // exclusive scan of digit_total over the first 256 threads (8 warps)
-        const uint32_t incl = warp_incl_scan_add(digit_total);
-        if (digit_thread && lane == 31) s.scan_tmp[warp] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const uint32_t w = threadIdx.x < kRadix / 32 ? s.scan_tmp[threadIdx.x] : 0;
-            const uint32_t wi = warp_incl_scan_add(w);
-            if (threadIdx.x < kRadix / 32) s.scan_tmp[threadIdx.x] = wi - w;
-        }
-        __syncthreads();
-        if (digit_thread) s.digit_local[threadIdx.x] = s.scan_tmp[warp] + incl - digit_total;
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 256 digit totals: 8 per lane
+        uint32_t v[kRadix / 32], sum = 0;
+#pragma unroll
+        for (int i = 0; i < kRadix / 32; ++i) { v[i] = s.digit_total[lane * (kRadix / 32) + i]; sum += v[i]; }
+        uint32_t run = warp_incl_scan_add(sum) - sum;
+#pragma unroll
+        for (int i = 0; i < kRadix / 32; ++i) { s.digit_local[lane * (kRadix / 32) + i] = run; run += v[i]; }
     }
     __syncthreads();
 
-    // stage the tile in digit order (the look-back of the digit threads follows, overlapping other CTAs' work)
+    // stage the tile in digit order (the look-back follows, overlapping other CTAs' work)
 #pragma unroll
-    for (int j = 0; j < kSwItems; ++j) {
+    for (int j = 0; j < kItems; ++j) {
         const uint32_t e = warp_base + j * 32 + lane;
         if (e < tile_count) {
             const uint32_t d = dg(key[j]);
             s.keys[s.digit_local[d] + s.warp_cnt[warp][d] + rank[j]] = key[j];
         }
     }
-    if (digit_thread && threadIdx.x <= mask) {
+    for (uint32_t d = threadIdx.x; d <= mask; d += kThreads) {
         uint32_t excl = 0;
         if (tile > 0) {
             uint32_t p = tile - 1;
             uint32_t spins = 0;
             while (true) {
                 uint32_t w;
-                asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(status + (size_t)p * kRadix + threadIdx.x) : "memory");
+                asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(status + (size_t)p * kRadix + d) : "memory");
                 if ((w >> 30) == 0) {             // predecessor has not ranked its keys yet
                     if (++spins > (1u << 28)) __trap();
                     continue;
@@ -353,20 +341,35 @@ __global__ void __launch_bounds__(kSwThreads, kSwMinBlocks) radix_sweep_kernel(c
                 if (w & kFlagPrefix) break;        // tile 0 always publishes PREFIX: p never underflows
                 --p;
             }
-            uint32_t *mine = status + (size_t)tile * kRadix + threadIdx.x;
-            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(mine), "r"(kFlagPrefix | (excl + digit_total)) : "memory");
+            uint32_t *mine = status + (size_t)tile * kRadix + d;
+            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(mine), "r"(kFlagPrefix | (excl + s.digit_total[d])) : "memory");
         }
-        s.digit_global[threadIdx.x] = digit_base[threadIdx.x] + excl - s.digit_local[threadIdx.x];
+        s.digit_global[d] = digit_base[d] + excl - s.digit_local[d];
     }
     __syncthreads();
 
     // contiguous runs out to global memory
-    for (uint32_t i = threadIdx.x; i < tile_count; i += kSwThreads) {
+    for (uint32_t i = threadIdx.x; i < tile_count; i += kThreads) {
         const uint64_t k = s.keys[i];
         const uint32_t d = dg(k);
         out[(uint64_t)(s.digit_global[d] + i)] = k;
     }
 }
+
+struct SweepGeom {
+    int threads, items;
+    size_t smem;
+    void (*k8)(const uint64_t *, uint64_t *, uint64_t, DigitSpec, const uint32_t *, uint32_t *, uint32_t *);
+    void (*k0)(const uint64_t *, uint64_t *, uint64_t, DigitSpec, const uint32_t *, uint32_t *, uint32_t *);
+};
+template <int kThreads, int kItems, int kMinBlocks>
+constexpr SweepGeom make_geom() {
+    return SweepGeom{kThreads, kItems, sizeof(SweepSmemT<kThreads, kItems>), radix_sweep_kernel<8, kThreads, kItems, kMinBlocks>,
+                     radix_sweep_kernel<0, kThreads, kItems, kMinBlocks>};
+}
+const SweepGeom kGeoms[] = {make_geom<512, 16, 2>(), make_geom<256, 16, 4>(), make_geom<256, 16, 3>(), make_geom<128, 16, 8>(),
+                            make_geom<256, 8, 6>(), make_geom<384, 16, 2>()};
+constexpr int kNumGeoms = sizeof(kGeoms) / sizeof(kGeoms[0]);
 
 }  // namespace
 
@@ -397,19 +400,21 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
     const bool legacy = n >= (1ull << 30) || n_passes > kMaxPasses || (sort_env && sort_env[0] == 'l');
     if (!ctx->sort_attr_set) {   // function attributes are per device: once per context, not per process
         KG_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-#define KG_SWEEP_ATTR(BITS, MATCH) \
-    KG_CUDA(ctx, cudaFuncSetAttribute(radix_sweep_kernel<BITS, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)))
-        KG_SWEEP_ATTR(8, 8); KG_SWEEP_ATTR(0, 8); KG_SWEEP_ATTR(8, 4); KG_SWEEP_ATTR(0, 4);
-        KG_SWEEP_ATTR(8, 2); KG_SWEEP_ATTR(0, 2); KG_SWEEP_ATTR(8, 0); KG_SWEEP_ATTR(0, 0);
-#undef KG_SWEEP_ATTR
+        for (int g = 0; g < kNumGeoms; ++g) {
+            KG_CUDA(ctx, cudaFuncSetAttribute(kGeoms[g].k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGeoms[g].smem));
+            KG_CUDA(ctx, cudaFuncSetAttribute(kGeoms[g].k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGeoms[g].smem));
+        }
         ctx->sort_attr_set = true;
     }
     const uint32_t n_tiles = ceil_div_u64(n, kRsTile);
     uint64_t *src = a, *dst = b;
-    const char *match_env = getenv("KOMBGPU_SORT_MATCH");   // items per thread ranked with MATCH.ANY (0, 2, 4, 8)
-    const int n_match = match_env ? atoi(match_env) : 0;
     if (!legacy) {
-        const uint32_t n_tiles = ceil_div_u64(n, kSwTile);
+        const char *tile_env = getenv("KOMBGPU_SORT_TILE");   // index into kGeoms (A/B runs)
+        int gi = tile_env ? atoi(tile_env) : 0;
+        if (gi < 0 || gi >= kNumGeoms) gi = 0;
+        const SweepGeom &geom = kGeoms[gi];
+        const uint32_t sw_tile = (uint32_t)(geom.threads * geom.items);
+        const uint32_t n_tiles = ceil_div_u64(n, sw_tile);
         // [n_passes x 256 digit histograms | n_passes tile counters | n_passes x n_tiles x 256 status words]
         const size_t head = (size_t)n_passes * kRadix + kMaxPasses;
         DevBuf<uint32_t> ws;
@@ -418,21 +423,16 @@ int radix_sort_u64(kombgpu_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const
         PassList pl{};
         pl.n = n_passes;
         for (int p = 0; p < n_passes; ++p) pl.dg[p] = DigitSpec::of(passes[p]);
-        const uint32_t hist_grid = min(n_tiles, (uint32_t)ctx->sm_count * 4u);
+        const uint32_t hist_grid = min(ceil_div_u64(n, kRsTile), (uint32_t)ctx->sm_count * 4u);
         KG_LAUNCH(ctx, radix_global_hist_kernel, hist_grid, kRsThreads, 0, src, n, pl, ws.p);
         KG_LAUNCH(ctx, radix_hist_scan_kernel, n_passes, kRadix, 0, ws.p);
         for (int p = 0; p < n_passes; ++p) {
             const uint32_t *dbase = ws.p + (size_t)p * kRadix;
             const bool w8 = passes[p].bits + passes[p].bits2 == 8;
             uint32_t *status = ws.p + head + (size_t)p * n_tiles * kRadix, *counter = ws.p + (size_t)n_passes * kRadix + p;
-#define KG_SWEEP(BITS, MATCH)                                                                                        \
-    KG_LAUNCH(ctx, (radix_sweep_kernel<BITS, MATCH>), n_tiles, kSwThreads, sizeof(SweepSmem), src, dst, n, pl.dg[p], \
-              dbase, status, counter)
-            if (n_match == 8) { if (w8) KG_SWEEP(8, 8); else KG_SWEEP(0, 8); }
-            else if (n_match == 4) { if (w8) KG_SWEEP(8, 4); else KG_SWEEP(0, 4); }
-            else if (n_match == 2) { if (w8) KG_SWEEP(8, 2); else KG_SWEEP(0, 2); }
-            else { if (w8) KG_SWEEP(8, 0); else KG_SWEEP(0, 0); }
-#undef KG_SWEEP
+            (w8 ? geom.k8 : geom.k0)<<<n_tiles, geom.threads, geom.smem, ctx->stream>>>(src, dst, n, pl.dg[p], dbase, status, counter);
+            ctx->launches++;
+            KG_CUDA(ctx, cudaPeekAtLastError());
             uint64_t *t = src; src = dst; dst = t;
         }
         *sorted = src;

@@ -1,5 +1,5 @@
 """Time the radix sort alone (kombgpu_debug_sort_u64) on the key shapes the path sorts:
-   sort_probe.py [legacy|sweep ...]"""
+   sort_probe.py [legacy|sweep|sweep@<geometry index> ...]"""
 import os, sys, ctypes, json
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -11,8 +11,8 @@ SHAPES = [("hits 20M (20+23 bits, reads in order)", 20_003_139, 20, 23, 1), ("pa
           ("swapped 33M (20 bits high)", 32_850_322, 0, 20, 0), ("corea 1M (26 bits high)", 1_000_000, 0, 26, 0),
           ("pairs 540M (26+26 bits)", 540_000_000, 26, 26, 0)]
 for mode in (sys.argv[1:] or ["legacy", "sweep"]):
-    os.environ["KOMBGPU_SORT"] = mode.split(":")[0]
-    os.environ["KOMBGPU_SORT_MATCH"] = mode.split(":")[1] if ":" in mode else "0"
+    os.environ["KOMBGPU_SORT"] = mode.split("@")[0]
+    os.environ["KOMBGPU_SORT_TILE"] = mode.split("@")[1] if "@" in mode else "0"
     for name, n, lo, hi, srt in SHAPES:
         ms, ok = ctypes.c_float(), ctypes.c_int()
         rc = lib.kombgpu_debug_sort_u64(ctx._h, n, lo, hi, srt, 3, ctypes.byref(ms), ctypes.byref(ok))
