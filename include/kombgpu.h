@@ -253,6 +253,18 @@ int kombgpu_graph_results_csr(kombgpu_graph *g, int key_mode, uint64_t *fwd_ptr,
 int kombgpu_graph_densest_core(kombgpu_graph *g, int32_t *k_star, uint32_t *n_vertices, uint64_t *n_edges,
                                double *density);
 
+/* Densest BLOCK: the greedy peel of CombineCoreA::runMerge (src/CombineCoreA.h:45-219, over HashIndexedMinHeap,
+ * src/HashIndexedMinHeap.h:10-238) in bulk form.  f(S) = sum of the unitigs' weights + edges inside S, density =
+ * f(S) / |S| (the reference's suspiciousSum / nodes left: both counted twice there, once per row / column copy),
+ * priority(v) = weight(v) + degree inside S.  The reference removes the minimum-priority node one at a time; here a
+ * pass removes every survivor with priority <= 2 (1 + eps) density(S) (at least an eps / (1 + eps) share of them),
+ * and the densest S seen is returned: a 2 (1 + eps)-approximation of the densest block (2 for the serial order), in
+ * O(log n / eps) passes, independent of any tie order.  `weight`: n_vertices host doubles >= 0 (the reference's
+ * `suspiciousness`), or NULL with use_scores != 0 for the graph's own CORE-A scores, or NULL / 0 for the unweighted
+ * peel.  member (optional): n_vertices bytes, 1 for the unitigs of the block.  Any output pointer may be NULL. */
+int kombgpu_graph_densest_block(kombgpu_graph *g, const double *weight, int use_scores, double eps, uint32_t *n_vertices,
+                                uint64_t *n_edges, double *weight_sum, double *density, uint32_t *n_passes, uint8_t *member);
+
 /* The maximal core and the trussness of its edges (needs kombgpu_coreness): the induced subgraph of the unitigs
  * whose coreness is the maximum, igraph_trussness of every edge of it (the largest k such that the edge lies in a
  * k-truss; 2 for an edge in no triangle) and the unitigs on the edges of maximal trussness -- what the reference's

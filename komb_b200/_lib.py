@@ -87,6 +87,8 @@ SIGNATURES = {
     "kombgpu_analyse_hits": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, POINTER(c_void_p)]),
     "kombgpu_graph_densest_core": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint64), POINTER(c_double)]),
+    "kombgpu_graph_densest_block": (c_int, [c_void_p, c_void_p, c_int, c_double, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_double),
+                                            POINTER(c_double), POINTER(c_uint32), c_void_p]),
     "kombgpu_graph_analyse": (c_int, [c_void_p, c_int]),
     "kombgpu_graph_max_core_truss": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_int32), POINTER(c_uint32)]),
     "kombgpu_graph_max_core_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -404,6 +404,20 @@ class Graph:
         self._ctx._check(self._lib.kombgpu_graph_densest_core(self._h, byref(k), byref(nv), byref(ne), byref(d)))
         return {"k": k.value, "n_vertices": nv.value, "n_edges": ne.value, "density": d.value}
 
+    def densest_block(self, weight=None, use_scores: bool = False, eps: float = 0.5) -> dict:
+        """Densest block by the bulk form of the reference's greedy peel (kombgpu_graph_densest_block): sizes, density
+        f(S) / |S| with f = weights + edges inside S, passes, and the block's membership mask."""
+        n, _ = self.counts()
+        nv, ne, ws, d, np_ = c_uint32(), c_uint64(), c_double(), c_double(), c_uint32()
+        member = np.zeros(n, np.uint8)
+        wt = _host(weight, np.float64) if weight is not None else None
+        if wt is not None and wt.shape != (n,):
+            raise ValueError("weight must hold one value per vertex")
+        self._ctx._check(self._lib.kombgpu_graph_densest_block(self._h, _ptr(wt) if wt is not None else None, int(bool(use_scores)), float(eps),
+                                                               byref(nv), byref(ne), byref(ws), byref(d), byref(np_), _ptr(member)))
+        return {"n_vertices": nv.value, "n_edges": ne.value, "weight_sum": ws.value, "density": d.value, "passes": np_.value,
+                "member": member.astype(bool)}
+
     def max_core_truss(self) -> dict:
         """Maximal core + trussness of its edges (kombgpu_graph_max_core_truss, reference Kgraph::runTruss): sizes, the
         induced edges (original ids) with their trussness, and the unitigs on edges of maximal trussness."""

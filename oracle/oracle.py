@@ -29,6 +29,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "libkomb_oracle.so"
 REF_KOMB2 = _HERE / "_ref" / "komb2_ref"
 REF_COREA = _HERE / "_ref" / "corea_ref"
+REF_DENSEST = _HERE / "_ref" / "densest_ref"
 
 KEY_REF32 = 0
 KEY_EXACT64 = 1
@@ -172,6 +173,65 @@ def densest_core(core: np.ndarray, edges: np.ndarray) -> dict:
         if best is None or d > best["density"] or (d == best["density"] and int(vk[k]) > best["n_vertices"]):
             best = {"k": k, "n_vertices": int(vk[k]), "n_edges": int(ek[k]), "density": d}
     return best
+
+
+def densest_block_bulk(n: int, edges: np.ndarray, weight=None, eps: float = 0.5) -> dict:
+    """Checker for kombgpu_graph_densest_block: the greedy densest-block peel of CombineCoreA::runMerge
+    (src/CombineCoreA.h:45-219) in bulk form.  f(S) = sum of weights + edges inside S, density = f(S) / |S|
+    (suspiciousSum / numOfNodesBelong, :133: both halved, a unitig's row and column copy always carry the same
+    priority on a symmetric adjacency); a pass removes every survivor with weight + degree inside S <= 2 (1 + eps)
+    density(S); the densest S seen wins (strict >, like :134)."""
+    u, v = unpack_edges(edges)
+    u, v = u.astype(np.int64), v.astype(np.int64)
+    w = np.zeros(n, np.float64) if weight is None else np.asarray(weight, np.float64)
+    alive = np.ones(n, bool)
+    deg = np.bincount(np.concatenate([u, v]), minlength=n).astype(np.int64) if n else np.zeros(0, np.int64)
+    W, E, N = float(w.sum()), int(edges.shape[0]), n
+    best = {"n_vertices": n, "n_edges": E, "weight_sum": W, "density": (W + E) / n if n else 0.0, "passes": 0, "member": alive.copy()}
+    t = 0
+    e_alive = np.ones(edges.shape[0], bool)
+    while N > 0:
+        rho = (W + float(E)) / float(N)
+        if t == 0 or rho > best["density"]:
+            best = {"n_vertices": N, "n_edges": E, "weight_sum": W, "density": rho, "member": alive.copy()}
+        thr = 2.0 * (1.0 + eps) * rho
+        take = alive & (w + deg.astype(np.float64) <= thr)
+        assert take.any()
+        alive &= ~take
+        gone = e_alive & (take[u] | take[v])
+        # survivors lose a neighbour for every edge towards a removed unitig
+        np.subtract.at(deg, u[gone & ~take[u]], 1)
+        np.subtract.at(deg, v[gone & ~take[v]], 1)
+        e_alive &= ~gone
+        N -= int(take.sum())
+        E -= int(gone.sum())
+        W -= float(w[take].sum())
+        if W < 0.0 or N == 0:
+            W = 0.0
+        t += 1
+    best["passes"] = t
+    return best
+
+
+def densest_block_greedy(n: int, edges: np.ndarray, weight, workdir) -> dict:
+    """The reference's serial greedy (CombineCoreA::runMerge, src/CombineCoreA.h:45-219) over the reference's own
+    HashIndexedMinHeap: oracle/_ref/densest_ref.  Density is in the reference's units, (2 sum w + 2 E(S)) / (rows +
+    columns left)."""
+    workdir = Path(workdir)
+    u, v = unpack_edges(edges)
+    with open(workdir / "densest_in.bin", "wb") as f:
+        f.write(np.array([n, 0 if weight is None else 1], dtype=np.int32).tobytes())
+        f.write(np.array([edges.shape[0]], dtype=np.int64).tobytes())
+        if weight is not None:
+            f.write(np.ascontiguousarray(weight, dtype=np.float64).tobytes())
+        f.write(u.astype(np.int32).tobytes())
+        f.write(v.astype(np.int32).tobytes())
+    subprocess.run([str(REF_DENSEST), str(workdir / "densest_in.bin"), str(workdir / "densest_out.bin")], check=True)
+    raw = (workdir / "densest_out.bin").read_bytes()
+    density = float(np.frombuffer(raw[:8], np.float64)[0])
+    nr, nc = (int(x) for x in np.frombuffer(raw[8:16], np.int32))
+    ids = np.frombuffer(raw[16:], np.int32)
+    return {"density": density, "rows": np.sort(ids[:nr]), "cols": np.sort(ids[nr:nr + nc])}
 
 
 def max_core_truss(n: int, edges: np.ndarray, core: np.ndarray) -> dict:

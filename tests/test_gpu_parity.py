@@ -487,3 +487,43 @@ def test_max_core_truss(ctx, oracle_mod):
 def komb_b200_key_exact():
     import komb_b200
     return komb_b200.KEY_EXACT64
+
+
+def test_densest_block(ctx, oracle_mod):
+    """kombgpu_graph_densest_block (the bulk form of CombineCoreA::runMerge's greedy peel) against the numpy checker:
+    block, sizes, density and pass count identical -- unweighted, with exact (dyadic) weights, with the graph's own
+    CORE-A scores (within rounding of the weight sums) -- plus known answers."""
+    import komb_b200
+    rng = np.random.default_rng(17)
+    for seed, scale, m, n in [(1, 12, 30_000, 3000), (2, 16, 600_000, 50_000), (3, 18, 2_000_000, 200_000)]:
+        us, vs = synth.rmat_edges(scale, m, n_vertices=n, seed=seed)
+        exp_edges = oracle_mod.simplify(us, vs)
+        w = rng.integers(0, 8192, n).astype(np.float64) / 1024.0      # every partial sum is exact in double
+        with ctx.graph_from_edges(us, vs, n) as g:
+            for weight, eps in ((None, 0.5), (None, 0.0), (w, 0.5), (w, 0.05)):
+                got = g.densest_block(weight=weight, eps=eps)
+                exp = oracle_mod.densest_block_bulk(n, exp_edges, weight, eps)
+                assert np.array_equal(got["member"], exp["member"])
+                assert {k: got[k] for k in ("n_vertices", "n_edges", "weight_sum", "density", "passes")} == \
+                       {k: exp[k] for k in ("n_vertices", "n_edges", "weight_sum", "density", "passes")}
+            with pytest.raises(komb_b200.KombGpuError):           # the scores do not exist yet
+                g.densest_block(use_scores=True)
+            g.coreness(); score = g.corea()
+            got = g.densest_block(use_scores=True, eps=0.5)
+            exp = oracle_mod.densest_block_bulk(n, exp_edges, score, 0.5)
+            assert got["n_vertices"] == exp["n_vertices"] and got["n_edges"] == exp["n_edges"] and got["passes"] == exp["passes"]
+            np.testing.assert_allclose(got["density"], exp["density"], rtol=1e-12)
+            with pytest.raises(komb_b200.KombGpuError):
+                g.densest_block(weight=-w)
+    # a K_40 planted in a sparse graph is the densest block: density 19.5
+    iu, iv = np.triu_indices(40, k=1)
+    u = np.concatenate([iu + 100, rng.integers(0, 30_000, 60_000)]).astype(np.uint32)
+    v = np.concatenate([iv + 100, rng.integers(0, 30_000, 60_000)]).astype(np.uint32)
+    with ctx.graph_from_edges(u, v, 30_000) as g:
+        got = g.densest_block(eps=0.1)
+        assert got["density"] >= 19.5 and set(np.flatnonzero(got["member"])) >= set(range(100, 140))
+    with ctx.graph_from_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 7) as g:
+        got = g.densest_block()
+        assert got["n_vertices"] == 7 and got["density"] == 0.0 and got["passes"] == 1 and got["member"].all()
+    with ctx.graph_from_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 0) as g:
+        assert g.densest_block()["n_vertices"] == 0

@@ -160,3 +160,48 @@ def test_truss_restatement_against_networkx(oracle_mod):
         assert got["max_trussness"] == k - 1
         top = nx.k_truss(sub, k - 1)
         assert sorted(x for x in top.nodes() if top.degree(x) > 0) == got["truss_vertices"].tolist()
+
+
+def _dyadic_weights(rng, n):
+    """multiples of 1/1024 below 8: every sum the peel forms is exact in double, whatever the order"""
+    return rng.integers(0, 8192, n).astype(np.float64) / 1024.0
+
+
+def test_densest_block_checkers(oracle_mod, tmp_path):
+    """The bulk densest-block checker (oracle.densest_block_bulk) against the reference's serial greedy run over the
+    reference's own HashIndexedMinHeap (oracle/_ref/densest_ref): both approximate the same optimum, so they bound
+    each other (bulk <= OPT_sym <= OPT_b <= 2 greedy; greedy <= OPT_b <= 2 OPT_sym <= 4 (1 + eps) bulk), and on a
+    planted clique both find it."""
+    if not oracle_mod.REF_DENSEST.exists():
+        pytest.skip("oracle/_ref/densest_ref not built (needs /root/reference)")
+    from komb_b200 import synth
+    rng = np.random.default_rng(11)
+    for seed, n, m, weighted in [(1, 200, 1500, False), (2, 800, 9000, True), (3, 50, 80, True), (4, 1500, 4000, False)]:
+        u, v = synth.rmat_edges(11, m, n_vertices=n, seed=seed)
+        edges = oracle_mod.simplify(u, v)
+        w = _dyadic_weights(rng, n) if weighted else None
+        for eps in (0.0, 0.5):
+            bulk = oracle_mod.densest_block_bulk(n, edges, w, eps)
+            greedy = oracle_mod.densest_block_greedy(n, edges, w, tmp_path)
+            assert bulk["density"] <= 2.0 * greedy["density"] * (1 + 1e-12)
+            assert greedy["density"] <= 4.0 * (1.0 + eps) * bulk["density"] * (1 + 1e-12)
+            # the reported density is the density of the reported block
+            mem = bulk["member"]
+            eu, ev = oracle_mod.unpack_edges(edges)
+            inside = int((mem[eu] & mem[ev]).sum())
+            ws = float(w[mem].sum()) if weighted else 0.0
+            assert bulk["n_vertices"] == int(mem.sum()) and bulk["n_edges"] == inside
+            assert bulk["density"] == (ws + inside) / mem.sum()
+    # K_30 planted in a sparse graph: the clique is the densest block for both (density (30 - 1) / 2)
+    iu, iv = np.triu_indices(30, k=1)
+    u = np.concatenate([iu + 7, rng.integers(0, 3000, 3000)]).astype(np.uint32)
+    v = np.concatenate([iv + 7, rng.integers(0, 3000, 3000)]).astype(np.uint32)
+    edges = oracle_mod.simplify(u, v)
+    bulk = oracle_mod.densest_block_bulk(3000, edges, None, 0.1)
+    greedy = oracle_mod.densest_block_greedy(3000, edges, None, tmp_path)
+    assert set(np.flatnonzero(bulk["member"])) >= set(range(7, 37)) and bulk["density"] >= 14.5
+    assert set(greedy["rows"]) >= set(range(7, 37)) and greedy["density"] >= 14.5
+    # degenerate inputs
+    assert oracle_mod.densest_block_bulk(0, np.zeros(0, np.uint64))["n_vertices"] == 0
+    one = oracle_mod.densest_block_bulk(5, np.zeros(0, np.uint64), np.array([0.0, 2.0, 0.5, 0.0, 0.0]), 0.5)
+    assert one["n_vertices"] == 1 and one["density"] == 2.0 and one["member"].tolist() == [False, True, False, False, False]
