@@ -119,7 +119,7 @@ def _komb2_run(binary, d: Path, outdir: Path, threads: int, env=None):
     return cp, wall
 
 
-def cpu_reference_run(n_unitigs: int, sample_read_pairs: int, seed: int, threads: int, dropin: bool = False) -> dict:
+def cpu_reference_run(n_unitigs: int, sample_read_pairs: int, seed: int, threads: int, dropin: bool = False, ctx=None) -> dict:
     from komb_b200 import synth
     from oracle import oracle
     m1, m2 = synth.metagenome_hits(n_unitigs, sample_read_pairs, seed=seed)
@@ -134,27 +134,48 @@ def cpu_reference_run(n_unitigs: int, sample_read_pairs: int, seed: int, threads
             synth.write_fasta(str(d / "u.fasta"), 4)
             cp, wall = _komb2_run(oracle.REF_KOMB2, d, d / "out", threads)
             drop = None
+            tok = None
+            if ctx is not None:
+                # the device tokeniser (kombgpu_sam_parse) on the same SAM text: bytes in, integer hits on the device
+                texts = [(d / "r1.sam").read_bytes(), (d / "r2.sam").read_bytes()]
+                best = None
+                for _ in range(3):
+                    with ctx.sam_parse(texts) as hits:
+                        c, tm = hits.counts(), hits.timing()
+                        if best is None or tm["ms_parse"] < best["ms_parse"]:
+                            best = dict(tm, **c)
+                nbytes = sum(len(t) for t in texts)
+                tok = {"sam_bytes": nbytes, "n_hits": best["n_hits"], "n_lines": best["n_lines"], "ms_upload_pageable": best["ms_upload"],
+                       "ms_parse_and_intern": best["ms_parse"], "kernel_launches": best["kernel_launches"],
+                       "parse_gb_per_s": nbytes / (best["ms_parse"] * 1e-3) / 1e9, "parse_hits_per_s": best["n_hits"] / (best["ms_parse"] * 1e-3),
+                       "hits_equal_generator": bool(best["n_hits"] == n_hits),
+                       "cpu_reading_sams_s": None}
             if dropin and (ROOT / "bin" / "komb2").exists():
                 # the drop-in executable on the SAME SAM pair: like for like (text in, three files out)
                 env = dict(os.environ, KOMB_TIMING="1")
-                walls, ctx_s = [], []
-                for _ in range(2):
+                walls, ctx_s, after_s = [], [], []
+                for _ in range(3):
                     cpd, w = _komb2_run(ROOT / "bin" / "komb2", d, d / "out_gpu", threads, env)
                     walls.append(w)
                     m = re.search(r"kombgpu_ctx_create \(joined\)\s+\+([0-9.]+) s \(at ([0-9.]+) s\)", cpd.stderr)
                     ctx_s.append(float(m.group(2)) if m else None)
+                    ends = re.findall(r"\(at ([0-9.]+) s\)", cpd.stderr)
+                    after_s.append(float(ends[-1]) - float(m.group(2)) if m and ends else None)
+                # the same executable with the host tokeniser / host writers (KOMB_TOKENIZE=host): the round-1 path
+                _, wall_host_tok = _komb2_run(ROOT / "bin" / "komb2", d, d / "out_gpu_host", threads, dict(env, KOMB_TOKENIZE="host"))
                 # parity target is the reference at -t 1 (at -t > 1 it silently drops SAM lines: SURVEY quirk Q1)
                 _, wall_t1 = _komb2_run(oracle.REF_KOMB2, d, d / "out_t1", 1)
                 ref_out, our_out = oracle.read_outputs(d / "out_t1"), oracle.read_outputs(d / "out_gpu")
                 same = (ref_out["kcore"] == our_out["kcore"] and ref_out["edges"] == our_out["edges"]
                         and all(abs(ref_out["score"][k] - our_out["score"][k]) <= 1e-6 * max(1.0, abs(ref_out["score"][k])) + 1e-6
                                 for k in ref_out["score"]))
-                drop = {"komb2_wall_s": walls, "device_ready_at_s": ctx_s, "komb2_ref_wall_s": wall, "komb2_ref_t1_wall_s": wall_t1,
+                drop = {"komb2_wall_s": walls, "device_ready_at_s": ctx_s, "work_after_context_s": after_s,
+                        "komb2_host_tokeniser_wall_s": wall_host_tok, "komb2_ref_wall_s": wall, "komb2_ref_t1_wall_s": wall_t1,
                         "threads": threads,
                         "speedup_wall": wall / min(walls), "outputs_equal_by_name": bool(same),
                         "note": "bin/komb2 vs komb2_ref on the same SAM pair; wall clock of the whole process including CUDA context "
-                                "creation (device_ready_at_s: when the context was usable; it is created on a helper thread "
-                                "while the host tokenises)"}
+                                "creation (device_ready_at_s: when the context was usable; work_after_context_s: SAM text to "
+                                "the three files once the device is up -- tokenised, interned and formatted on the device)"}
         stages = {m.group(1).strip(): float(m.group(2))
                   for m in re.finditer(r"Time elapsed (?:for|doing) ([^:]+): ([0-9.]+) s", cp.stdout)}
         total = stages.get("KOMB", wall)          # komb2's own end-to-end timer (komb2.cpp:141-143)
@@ -164,7 +185,8 @@ def cpu_reference_run(n_unitigs: int, sample_read_pairs: int, seed: int, threads
                 "sample": sample + f"; komb2_ref -t {threads} from SAM text, {total:.2f} s (igraph stages are the shim's)",
                 "seconds": total, "n_hits": n_hits, "n_edges": edges,
                 "peel_edges_per_s": (edges / kcore_s) if kcore_s else None,
-                "stage_seconds": stages, "dropin": drop}
+                "stage_seconds": stages, "dropin": drop,
+                "tokenise": dict(tok, cpu_reading_sams_s=stages.get("reading SAMs")) if tok else None}
     # port: the C restatement (single thread)
     rk = np.concatenate([m1.read_key, m2.read_key]); ut = np.concatenate([m1.unitig, m2.unitig])
     t0 = time.perf_counter()
@@ -178,7 +200,48 @@ def cpu_reference_run(n_unitigs: int, sample_read_pairs: int, seed: int, threads
             "sample": sample + "; oracle/komb_oracle.c from integer hits (no SAM parsing)",
             "seconds": t3 - t0, "n_hits": n_hits, "n_edges": int(edges.shape[0]),
             "peel_edges_per_s": edges.shape[0] / (t2 - t1), "stage_seconds": {"build": t1 - t0, "peel": t2 - t1, "corea": t3 - t2},
-            "dropin": None}
+            "dropin": None, "tokenise": None}
+
+
+def cpu_stage_samples(core: np.ndarray, deg: np.ndarray, hbm_note: str = "") -> dict:
+    """SURVEY 8(d) "CPU reference timing" for the stages komb2's own timers do not isolate: igraph's single-threaded
+    create/simplify/coreness on an R-MAT sample (the BZ port: the shim's igraph_coreness is the same algorithm), and
+    CoreA::getAnomalyScore straight from the reference's CoreA.h, which is O(n x distinct keys): timed at n <= 10^6 and
+    extrapolated above, next to an O(n log n) restatement."""
+    from oracle import oracle
+    import torch
+    out = {}
+    n = int(core.shape[0])
+    n_keys = int(np.unique(core.astype(np.int64) * n + deg).shape[0])
+    t0 = time.perf_counter()
+    oracle.corea(core, deg, oracle.KEY_REF32)
+    t_port = time.perf_counter() - t0
+    out["corea"] = {"n": n, "distinct_keys": n_keys, "port_nlogn_s": t_port, "port_vertices_per_s": n / t_port}
+    if oracle.REF_COREA.exists():
+        with tempfile.TemporaryDirectory() as d:
+            m = min(n, 1_000_000)
+            t0 = time.perf_counter()
+            oracle.corea_reference(core[:m], deg[:m], d)
+            t_ref = time.perf_counter() - t0
+        out["corea"].update({"reference_coreA_h_n": m, "reference_coreA_h_s": t_ref, "reference_vertices_per_s": m / t_ref,
+                             "reference_note": "CoreA.h fractionalRank is O(n x distinct keys): cfg3 (50 M unitigs, ~10^6 distinct "
+                                               "keys) is DNF on the CPU (extrapolated: > 10^4 x this time); the O(n log n) port is the "
+                                               "fair CPU number"})
+    # igraph create + simplify + coreness, single thread, on an R-MAT sample of cfg3's generator (scale 22 -> 2.5 M unitigs)
+    u, v = rmat_device(22, 40_000_000, 2_500_000, 42)
+    uh, vh = u.cpu().numpy().view(np.uint32), v.cpu().numpy().view(np.uint32)
+    del u, v
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    edges = oracle.simplify(uh, vh)
+    t1 = time.perf_counter()
+    oracle.coreness(2_500_000, edges)
+    t2 = time.perf_counter()
+    E = int(edges.shape[0])
+    out["rmat_sample"] = {"workload": "R-MAT scale 22, 40 M draws over 2.5 M unitigs (cfg3's generator at 1/13 size), one thread",
+                          "n_edges": E, "simplify_s": t1 - t0, "coreness_bz_s": t2 - t1, "build_edges_per_s": E / (t1 - t0),
+                          "peel_edges_per_s": E / (t2 - t1)}
+    return out
 
 
 def run_reference_arm(args):
@@ -534,11 +597,16 @@ def run_ours(args):
                 line["configs"][name] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_cpu_baseline:
         try:
-            cb = cpu_reference_run(N_UNITIGS, CPU_SAMPLE_READ_PAIRS, SEED, os.cpu_count() or 1, dropin=True)
+            cb = cpu_reference_run(N_UNITIGS, CPU_SAMPLE_READ_PAIRS, SEED, os.cpu_count() or 1, dropin=True, ctx=ctx)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["peel_edges_per_s"] = cb.get("peel_edges_per_s")
             line["cpu_baseline"]["stage_seconds"] = cb.get("stage_seconds")
             line["dropin"] = cb.get("dropin")
+            line["stages"]["tokenise"] = cb.get("tokenise")
+            try:
+                line["cpu_baseline"]["stage_samples"] = cpu_stage_samples(np.array(r_e2e["coreness"]), np.array(r_e2e["degree"]))
+            except Exception as e:
+                line["cpu_baseline"]["stage_samples"] = {"error": f"{type(e).__name__}: {e}"}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "hits/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)

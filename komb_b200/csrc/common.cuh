@@ -40,6 +40,7 @@ struct kombgpu_ctx {
     void *pinned = nullptr;             // small pinned staging area for scalar read-backs
     size_t pinned_bytes = 0;
     bool sort_attr_set = false;         // function attributes are per device: set once per context (sort.cu)
+    bool corea_attr_set = false;        // same for the CORE-A pair histogram (corea.cu)
     bool peer_attr_set = false;         // same for the partitioned peel kernel (ppeel.cu)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // stage timers (capi.cu StageTimer): created once
 };

@@ -11,6 +11,7 @@
 // Ranks are exact half-integers in FP64 (class [s, e) of the ascending order has
 // descending average rank n - (s + e - 1) / 2); only ln() can differ from glibc,
 // by <= 1 ulp, far inside the 1e-6 relative tolerance the path is held to.
+#include <cstdlib>
 #include <cstring>
 
 #include "dgraph.cuh"
@@ -165,6 +166,63 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const uint64_t *__restr
     if (lane_id() == 0 && bits) atomicMax(max_bits, bits);
 }
 
+// ---- small key spaces: no sort at all.  When (max coreness + 1) x (max degree + 1) is small (the usual unitig graph:
+// a few dozen coreness levels, a few hundred degrees) the (coreness, degree) pairs are counted in a 2-D histogram;
+// without int32 wrap the key coreness * n + degree orders like the pair, so the key ranks are a prefix scan over the
+// bins (the same LUT trick as the degree ranks, whose histogram is the bins' column sums).
+constexpr uint32_t kPairBinsSmem = 12288;        // 48 KB of shared-memory counters
+constexpr uint64_t kPairBinsMax = 1ull << 22;    // above this the sort-based path is used
+
+__global__ void __launch_bounds__(kThreads) pair_hist_kernel(const int32_t *__restrict__ core, const int32_t *__restrict__ deg, uint32_t n,
+                                                             uint32_t n_deg, uint32_t n_bins, uint32_t *__restrict__ hist) {
+    extern __shared__ uint32_t s_pair[];
+    const bool use_smem = n_bins <= kPairBinsSmem;
+    if (use_smem) {
+        for (uint32_t b = threadIdx.x; b < n_bins; b += kThreads) s_pair[b] = 0;
+        __syncthreads();
+    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)core[i] * n_deg + (uint32_t)deg[i];
+        if (use_smem) atomicAdd(&s_pair[b], 1u);
+        else atomicAdd(&hist[b], 1u);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < n_bins; b += kThreads) {
+            const uint32_t c = s_pair[b];
+            if (c) atomicAdd(&hist[b], c);
+        }
+    }
+}
+// degree histogram = column sums of the pair histogram
+__global__ void __launch_bounds__(kThreads) pair_hist_columns_kernel(const uint32_t *__restrict__ pair, uint32_t n_core, uint32_t n_deg,
+                                                                     uint32_t *__restrict__ deg_hist) {
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < n_deg; d += gridDim.x * blockDim.x) {
+        uint32_t s = 0;
+        for (uint32_t c = 0; c < n_core; ++c) s += pair[(uint64_t)c * n_deg + d];
+        deg_hist[d] = s;
+    }
+}
+__global__ void __launch_bounds__(kThreads) score_lut_kernel(const int32_t *__restrict__ core, const int32_t *__restrict__ deg, uint32_t n,
+                                                             uint32_t n_deg, const double *__restrict__ deg_lut,
+                                                             const double *__restrict__ key_lut, double *__restrict__ score,
+                                                             unsigned long long *__restrict__ max_bits) {
+    double local_max = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = (uint32_t)deg[i];
+        const double sc = fabs(log(deg_lut[d]) - log(key_lut[(uint64_t)(uint32_t)core[i] * n_deg + d]));
+        score[i] = sc;
+        local_max = fmax(local_max, sc);
+    }
+    unsigned long long bits = (unsigned long long)__double_as_longlong(local_max);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(kFullMask, bits, o);
+        bits = t > bits ? t : bits;
+    }
+    if (lane_id() == 0 && bits) atomicMax(max_bits, bits);
+}
+
 }  // namespace
 
 int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint32_t n, int key_mode, double *score,
@@ -183,6 +241,39 @@ int corea_scores(kombgpu_ctx *ctx, const int32_t *core, const int32_t *deg, uint
     KG_TRY(read_back(ctx, mm.p, h_mm, 3));
     if (h_mm[2]) return ctx_fail(ctx, KOMBGPU_EINVAL, "negative coreness or degree");
     const uint32_t max_deg = (uint32_t)h_mm[0], max_core = (uint32_t)h_mm[1];
+
+    // small key space and no int32 wrap of coreness * n + degree: ranks from the 2-D histogram, no sort
+    const uint64_t n_pair_bins = (uint64_t)(max_core + 1) * (uint64_t)(max_deg + 1);
+    // ref32 keys order like the pair only while coreness * n + degree neither wraps nor lets a degree >= n carry into the coreness
+    const bool wraps = key_mode == KOMBGPU_KEY_REF32 && ((uint64_t)max_core * n + max_deg > 0x7fffffffull || max_deg >= n);
+    const bool no_lut = getenv("KOMBGPU_COREA_SORT") != nullptr;   // A/B runs and tests: force the sort-based path
+    if (n_pair_bins <= kPairBinsMax && !wraps && !no_lut) {
+        const uint32_t n_deg = max_deg + 1, n_core = max_core + 1, nb = (uint32_t)n_pair_bins;
+        DevBuf<uint32_t> pair, dh;
+        DevBuf<double> key_lut, deg_lut;
+        DevBuf<unsigned long long> max_bits(ctx, 1);
+        KG_ALLOC(ctx, pair, nb);
+        KG_ALLOC(ctx, dh, n_deg);
+        KG_ALLOC(ctx, key_lut, nb);
+        KG_ALLOC(ctx, deg_lut, n_deg);
+        if (!max_bits) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+        KG_CUDA(ctx, cudaMemsetAsync(pair.p, 0, (size_t)nb * sizeof(uint32_t), ctx->stream));
+        KG_CUDA(ctx, cudaMemsetAsync(max_bits.p, 0, sizeof(unsigned long long), ctx->stream));
+        if (!ctx->corea_attr_set) {
+            KG_CUDA(ctx, cudaFuncSetAttribute(pair_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPairBinsSmem * sizeof(uint32_t))));
+            ctx->corea_attr_set = true;
+        }
+        const size_t smem = nb <= kPairBinsSmem ? (size_t)nb * sizeof(uint32_t) : 0;
+        KG_LAUNCH(ctx, pair_hist_kernel, grid_for(n, kThreads * 8, (uint32_t)ctx->sm_count * 2u), kThreads, smem, core, deg, n, n_deg, nb, pair.p);
+        KG_LAUNCH(ctx, pair_hist_columns_kernel, grid_for(n_deg, kThreads, cap), kThreads, 0, pair.p, n_core, n_deg, dh.p);
+        KG_TRY((device_scan<uint32_t>(ctx, n_deg, HistIn{dh.p}, RankLutOut{deg_lut.p, n}, (uint32_t *)nullptr)));
+        KG_TRY((device_scan<uint32_t>(ctx, nb, HistIn{pair.p}, RankLutOut{key_lut.p, n}, (uint32_t *)nullptr)));
+        KG_LAUNCH(ctx, score_lut_kernel, grid_for(n, kThreads, cap), kThreads, 0, core, deg, n, n_deg, deg_lut.p, key_lut.p, score, max_bits.p);
+        unsigned long long h_bits = 0;
+        KG_TRY(read_back(ctx, max_bits.p, &h_bits, 1));
+        memcpy(max_score_host, &h_bits, sizeof(double));
+        return KOMBGPU_OK;
+    }
 
     // degree ranks through a histogram LUT
     const uint32_t n_bins = max_deg + 1;
