@@ -23,6 +23,10 @@ struct kombgpu_dist_graph {
     // (By symmetry this is the transpose of the rank's rows: when x is peeled, these are the degrees this rank decrements.)
     uint32_t *nbr_ptr = nullptr;   // [n_global + 1]
     uint32_t *nbr = nullptr;       // [n_directed]
+    // ... or, for the asynchronous peel (apeel.cu), as the rank's ROWS: col[row_ptr32[u] .. row_ptr32[u + 1]) are the global
+    // ids of the neighbours of local unitig u (rows need no order inside).  A build makes one of the two layouts.
+    uint32_t *row_ptr32 = nullptr; // [n_local + 1]
+    uint32_t *col = nullptr;       // [n_directed]
     int32_t *deg = nullptr;        // [n_local]
     int32_t *core = nullptr;       // [n_local] after the peel
     double *score = nullptr;       // [n_local] after CORE-A
@@ -43,6 +47,10 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
 int route_keys(kombgpu_comm *c, const uint64_t *keys, uint64_t n, uint32_t step, bool rebase, uint64_t **recv, uint64_t *n_recv);
 // ppeel.cu
 int dist_peel(kombgpu_dist_graph *g);
+// apeel.cu
+int dist_peel_async(kombgpu_dist_graph *g);
+// which peel a build prepares for: KOMBGPU_DIST_PEEL=log (ranks meet once per cascade generation, ppeel.cu) or async (default)
+bool dist_peel_is_async();
 // pcorea.cu
 int dist_corea(kombgpu_dist_graph *g, int key_mode);
 

@@ -11,6 +11,8 @@
 //   owner         forward and backward entries together, keyed by the NEIGHBOUR and sorted on it: for every unitig x of
 //                 the graph the list of local unitigs adjacent to x -- the form the partitioned peel walks (ppeel.cu)
 // The only host round trips are the two count exchanges (the receive sizes have to be known to allocate).
+#include <cstdlib>
+
 #include "dgraph.cuh"
 #include "primitives.cuh"
 
@@ -131,21 +133,25 @@ __global__ void __launch_bounds__(kThreads) swap_edges_kernel(const uint64_t *__
 
 // the local adjacency entries keyed by the neighbour: entry i < n_fwd is the forward edge (u, v) -> (v << 32 | u - v_lo);
 // entry n_fwd + j is arrival j ((u - v_lo) << 32 | w) -> (w << 32 | u - v_lo), and counts one backward neighbour of u
+// by_row: the keys are (u - v_lo) << 32 | neighbour instead (the rank's rows, for the asynchronous peel)
 __global__ void __launch_bounds__(kThreads) nbr_keys_kernel(const uint64_t *__restrict__ edges, uint64_t n_fwd, const uint64_t *__restrict__ back,
-                                                            uint64_t n_back, uint32_t v_lo, uint32_t n_local, uint32_t n_global,
+                                                            uint64_t n_back, uint32_t v_lo, uint32_t n_local, uint32_t n_global, bool by_row,
                                                             uint64_t *__restrict__ keys, int32_t *__restrict__ back_cnt, uint32_t *__restrict__ err) {
     const uint64_t total = n_fwd + n_back;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t u, w;
         if (i < n_fwd) {
             const uint64_t e = edges[i];
-            keys[i] = ((uint64_t)(uint32_t)e << 32) | (uint64_t)((uint32_t)(e >> 32) - v_lo);
+            u = (uint32_t)(e >> 32) - v_lo;
+            w = (uint32_t)e;
         } else {
             const uint64_t s = back[i - n_fwd];
-            const uint32_t u = (uint32_t)(s >> 32), w = (uint32_t)s;
+            u = (uint32_t)(s >> 32);
+            w = (uint32_t)s;
             if (u >= n_local || w >= n_global) { atomicExch(err, 2u); keys[i] = 0; continue; }   // a mis-routed entry must not write past the arrays
-            keys[i] = ((uint64_t)w << 32) | u;
             atomicAdd(&back_cnt[u], 1);
         }
+        keys[i] = by_row ? (((uint64_t)u << 32) | w) : (((uint64_t)w << 32) | u);
     }
 }
 
@@ -182,6 +188,11 @@ struct EvTimer {   // CUDA-event split timer on the context's stream
 };
 
 }  // namespace
+
+bool dist_peel_is_async() {
+    const char *e = getenv("KOMBGPU_DIST_PEEL");
+    return !(e && e[0] == 'l');
+}
 
 int route_keys(kombgpu_comm *c, const uint64_t *keys, uint64_t n, uint32_t step, bool rebase, uint64_t **recv, uint64_t *n_recv) {
     kombgpu_ctx *ctx = c->ctx;
@@ -325,21 +336,23 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(deg.p, 0, (size_t)(n_local ? n_local : 1) * sizeof(int32_t), ctx->stream));
     KG_TRY(row_starts(ctx, edges.p, n_fwd, g->v_lo, n_local, n_global, fwd_start.p, d_err.p));
+    const bool by_row = dist_peel_is_async();
     if (n_dir)
         KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
-                  n_global, keys_a.p, deg.p, d_err.p);
+                  n_global, by_row, keys_a.p, deg.p, d_err.p);
     if (n_local)
         KG_LAUNCH(ctx, pdegree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, fwd_start.p, n_local, deg.p, max_deg.p);
     uint64_t *nsorted = keys_a.p;
     {
         RadixPass passes[8];
-        const int np = plan_radix_passes(32, 32 + bn, 0, 0, passes);
+        const int np = plan_radix_passes(32, 32 + (by_row ? bits_for(n_local > 0 ? n_local - 1 : 0) : bn), 0, 0, passes);
         KG_TRY(radix_sort_u64(ctx, keys_a.p, keys_b.p, n_dir, passes, np, &nsorted));
     }
     g->st.ms_build_sort += split.lap();
-    KG_ALLOC(ctx, nbr_ptr, (size_t)n_global + 1);
+    KG_ALLOC(ctx, nbr_ptr, (size_t)(by_row ? n_local : n_global) + 1);
     KG_ALLOC(ctx, nbr, n_dir);
-    KG_TRY(row_starts(ctx, nsorted, n_dir, 0u, n_global, n_local ? n_local : 1u, nbr_ptr.p, d_err.p));
+    if (by_row) KG_TRY(row_starts(ctx, nsorted, n_dir, 0u, n_local, n_global ? n_global : 1u, nbr_ptr.p, d_err.p));
+    else KG_TRY(row_starts(ctx, nsorted, n_dir, 0u, n_global, n_local ? n_local : 1u, nbr_ptr.p, d_err.p));
     if (n_dir) KG_LAUNCH(ctx, low_words_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, nsorted, n_dir, nbr.p);
     uint32_t h_err = 0;
     int32_t h_max = 0;
@@ -372,8 +385,8 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     g->edges = edges.take();
     g->mult = mult.take();
     g->fwd_start = fwd_start.take();
-    g->nbr_ptr = nbr_ptr.take();
-    g->nbr = nbr.take();
+    if (by_row) { g->row_ptr32 = nbr_ptr.take(); g->col = nbr.take(); }
+    else { g->nbr_ptr = nbr_ptr.take(); g->nbr = nbr.take(); }
     g->deg = deg.take();
     g->st.ms_build = total.lap();
     return KOMBGPU_OK;
@@ -382,10 +395,10 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
 void dist_graph_release(kombgpu_dist_graph *g) {
     if (!g || !g->ctx) return;
     kombgpu_ctx *ctx = g->ctx;
-    void *ptrs[] = {g->edges, g->mult, g->fwd_start, g->nbr_ptr, g->nbr, g->deg, g->core, g->score};
+    void *ptrs[] = {g->edges, g->mult, g->fwd_start, g->nbr_ptr, g->nbr, g->row_ptr32, g->col, g->deg, g->core, g->score};
     for (void *p : ptrs)
         if (p) ws_free(ctx, p);
-    g->edges = nullptr; g->mult = nullptr; g->fwd_start = nullptr; g->nbr_ptr = nullptr; g->nbr = nullptr;
+    g->edges = nullptr; g->mult = nullptr; g->fwd_start = nullptr; g->nbr_ptr = nullptr; g->nbr = nullptr; g->row_ptr32 = nullptr; g->col = nullptr;
     g->deg = nullptr; g->core = nullptr; g->score = nullptr;
 }
 

@@ -112,10 +112,14 @@ def _check(oracle, parts, case, key_mode):
     return parts
 
 
+@pytest.mark.parametrize("peel", ["async", "log"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("case", ["hits_small", "hits_mid", "rmat", "ramp", "hubs", "empty"])
-def test_peer_path_emulated_ranks(oracle_mod, case, world):
+def test_peer_path_emulated_ranks(oracle_mod, monkeypatch, case, world, peel):
+    """peel: the asynchronous peel (apeel.cu: remote atomics on the owners' degrees, discoveries pushed into the owners'
+    pools, ranks meet once per level) or the log-based one (ppeel.cu: ranks meet once per cascade generation)."""
     from komb_b200.peer import run_local
+    monkeypatch.setenv("KOMBGPU_DIST_PEEL", peel)
     key_mode = oracle_mod.KEY_EXACT64 if case in ("rmat", "ramp") else oracle_mod.KEY_REF32
     parts = run_local(world, lambda comm: _rank_body(comm, case, key_mode))
     parts = _check(oracle_mod, parts, case, key_mode)
