@@ -42,6 +42,7 @@ constexpr int kAScanItems = 4;
 constexpr unsigned long long kAEmpty = ~0ull;
 constexpr unsigned long long kASliceFlag = 1ull << 63;   // entry = flag | piece << 32 | local id ; else k << 32 | local id
 constexpr unsigned long long kAWatchdogNs = 20ull * 1000000000ull;
+constexpr int kALvlProf = 48;
 
 enum : uint32_t { kPhMin = 1, kPhScan = 2, kPhGo = 3, kPhExit = 4 };
 
@@ -57,7 +58,7 @@ struct ACtl {
 
 struct AState {   // local to a rank
     unsigned long long q_head;                 // tickets handed out
-    unsigned long long phase_word;             // seq << 8 | type
+    unsigned long long phase_word;             // seq << 40 | type << 32 | level (of a SCAN / GO)
     unsigned long long phase_done;             // worker CTAs that finished a phase (cumulative)
     unsigned long long n_visited, n_remote_dec, n_remote_push, n_slices, n_own_push;   // own: pushed into the own pool (scan, local discoveries, slices)
     unsigned long long prof_ns[6];             // manager: 0 min pass, 1 min exchange, 2 scan pass, 3 scan exchange, 4 level (go -> over)
@@ -65,6 +66,8 @@ struct AState {   // local to a rank
     uint32_t n_alive, alive_src;               // parameters of the current phase: list length, list index (2 = identity)
     int32_t local_min, cur_k, prev_k, max_core;
     uint32_t levels, error;                    // error: 1 watchdog (workers), 2 watchdog (peers), 5 pool overflow
+    uint32_t lvl_ns[kALvlProf], lvl_pushed[kALvlProf];   // first levels: time from GO to the end of the level, entries this rank processed
+    int32_t lvl_k[kALvlProf];
 };
 
 struct ARank {
@@ -115,6 +118,7 @@ __device__ __forceinline__ int32_t a_ld_deg(const int32_t *p) {
 __device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, uint32_t hi, int32_t k) {
     const uint32_t lane = lane_id();
     unsigned long long n_remote = 0, n_push = 0, n_own = 0;
+    int32_t left = INT32_MAX;   // smallest degree above k this walk left behind
     for (uint32_t base = lo; base < hi; base += 32u * kAU) {
         uint32_t own[kAU], li[kAU];
         int32_t old[kAU];
@@ -137,6 +141,9 @@ __device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, 
             }
         }
 #pragma unroll
+        for (int t = 0; t < kAU; ++t)
+            if (old[t] > k + 1) left = min(left, old[t] - 1);
+#pragma unroll
         for (int t = 0; t < kAU; ++t) {
             if (old[t] == k + 1) {   // this decrement took the unitig to level k: it is peeled now, by its owner
                 const unsigned long long tk = atomicAdd_system(&R.ctl_peer[own[t]]->q_tail, 1ull);
@@ -150,12 +157,15 @@ __device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, 
     n_remote = warp_reduce_add(n_remote);
     n_push = warp_reduce_add(n_push);
     n_own = warp_reduce_add(n_own);
+    left = warp_reduce_min(left);
     __syncwarp();
     if (lane == 0) {
         atomicAdd(&st->n_visited, (unsigned long long)(hi - lo));
         if (n_remote) atomicAdd(&st->n_remote_dec, n_remote);
         if (n_push) atomicAdd(&st->n_remote_push, n_push);
         if (n_own) atomicAdd(&st->n_own_push, n_own);
+        if (left != INT32_MAX) atomicMin(&st->local_min, left);
+        __threadfence();   // the bound is in place before this entry counts as done (the manager reads it after the level's end)
         // every decrement of this entry has returned and every unitig it discovered is counted in its owner's tail
         atomicAdd_system(&R.ctl_peer[R.rank]->q_done, 1ull);
     }
@@ -202,8 +212,8 @@ __device__ __forceinline__ void a_phase_min(const ARank &R, AState *st, uint32_t
     const int32_t *deg = R.deg_peer[R.rank];
     int32_t m = INT32_MAX;
     for (uint64_t i = (uint64_t)wcta * kAThreads + threadIdx.x; i < n; i += (uint64_t)n_wctas * kAThreads) {
-        const uint32_t v = src < 2u ? R.alive[src][i] : (uint32_t)i;
-        const int32_t d = a_ld_deg(&deg[v]);
+        const uint32_t v = src < 2u ? __ldcg(&R.alive[src][i]) : (uint32_t)i;
+        const int32_t d = __ldcg(&deg[v]);
         if (d > prev_k) m = min(m, d);
     }
     m = warp_reduce_min(m);
@@ -219,18 +229,21 @@ __device__ __forceinline__ void a_phase_scan(const ARank &R, AState *st, uint32_
     const uint32_t tid = threadIdx.x;
     const uint32_t tile = kAThreads * kAScanItems;
     unsigned long long *pool = R.pool_peer[R.rank];
+    int32_t surv_min = INT32_MAX;
     for (uint64_t t0 = (uint64_t)wcta * tile; t0 < n; t0 += (uint64_t)n_wctas * tile) {
         uint32_t v[kAScanItems], flag[kAScanItems], mine = 0;
+        int32_t d[kAScanItems];
+#pragma unroll
+        for (int j = 0; j < kAScanItems; ++j) {   // ids first, then every degree: two round trips per tile, not two per item
+            const uint64_t i = t0 + (uint64_t)j * kAThreads + tid;
+            v[j] = i < n ? (src < 2u ? __ldcg(&R.alive[src][i]) : (uint32_t)i) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int j = 0; j < kAScanItems; ++j) d[j] = v[j] != 0xffffffffu ? __ldcg(&deg[v[j]]) : INT32_MIN;
 #pragma unroll
         for (int j = 0; j < kAScanItems; ++j) {
-            const uint64_t i = t0 + (uint64_t)j * kAThreads + tid;
-            flag[j] = 0;
-            v[j] = 0;
-            if (i < n) {
-                v[j] = src < 2u ? R.alive[src][i] : (uint32_t)i;
-                const int32_t d = a_ld_deg(&deg[v[j]]);
-                flag[j] = d == k ? 1u : (d > k ? 0x10000u : 0u);
-            }
+            flag[j] = d[j] == k ? 1u : (d[j] > k ? 0x10000u : 0u);
+            if (d[j] > k) surv_min = min(surv_min, d[j]);
             mine += flag[j];
         }
         uint32_t total = 0;
@@ -256,13 +269,19 @@ __device__ __forceinline__ void a_phase_scan(const ARank &R, AState *st, uint32_
         }
         __syncthreads();
     }
+    surv_min = warp_reduce_min(surv_min);
+    if (lane_id() == 0 && surv_min != INT32_MAX) atomicMin(&st->local_min, surv_min);
 }
 
 __device__ void a_worker(const ARank &R, uint32_t wcta, uint32_t n_wctas, uint32_t *s_scan, uint32_t *s_base, unsigned long long *s_base64) {
     AState *st = R.st;
     const uint32_t lane = lane_id();
     unsigned long long seen = 0;    // sequence number of the last phase word handled
-    bool armed = false;             // decrements allowed (between GO and the next MIN)
+    int32_t go_k = -1;              // the level this warp has seen released (GO): unitigs of that level may be peeled.  A scan
+                                    // pushes its level's first unitigs BEFORE every rank's scan is complete; a warp that still
+                                    // holds the previous level's release must not touch them (a decrement next to a scan in
+                                    // progress peels a unitig twice).
+    bool armed = false;             // between a GO and the next scan
     const unsigned long long *pool = R.pool_peer[R.rank];
     while (true) {
         unsigned long long t = 0;
@@ -274,14 +293,18 @@ __device__ void a_worker(const ARank &R, uint32_t wcta, uint32_t n_wctas, uint32
         while (true) {
             if (armed && t < R.pool_cap) {
                 entry = a_ld_sys(pool + t);
-                if (entry != kAEmpty) break;
+                // a slice only exists once its unitig's level was released; a unitig carries its level
+                if (entry != kAEmpty && ((entry & kASliceFlag) || (int32_t)((entry >> 32) & 0x7fffffffu) == go_k)) break;
+                if ((++spins & 3u) != 0) continue;
             }
-            const unsigned long long pw = a_ld_acq(&st->phase_word);
-            if ((pw >> 8) != seen) {
-                const uint32_t type = (uint32_t)(pw & 0xffu);
+            unsigned long long pw = *(volatile unsigned long long *)&st->phase_word;
+            if ((pw >> 40) != seen) {
+                pw = a_ld_acq(&st->phase_word);   // the phase's parameters were written before the word
+                const uint32_t type = (uint32_t)(pw >> 32) & 0xffu;
                 if (type == kPhExit) return;
                 if (type == kPhGo) {
                     armed = true;
+                    go_k = (int32_t)(uint32_t)pw;
                 } else {
                     // MIN / SCAN are run by the whole CTA: every warp of it is in this loop (phases start when nothing is in flight)
                     armed = false;
@@ -294,11 +317,11 @@ __device__ void a_worker(const ARank &R, uint32_t wcta, uint32_t n_wctas, uint32
                         atomicAdd(&st->phase_done, 1ull);
                     }
                 }
-                seen = pw >> 8;
+                seen = pw >> 40;
                 t0 = a_ns();   // the peel is moving: the watchdog measures silence, not the length of the peel
                 continue;
             }
-            if ((++spins & 255u) == 0) {
+            if ((++spins & 1023u) == 0) {
                 if (*(volatile uint32_t *)&st->error) return;
                 if (a_ns() - t0 > kAWatchdogNs) { atomicCAS(&st->error, 0u, 1u); return; }
             }
@@ -309,10 +332,10 @@ __device__ void a_worker(const ARank &R, uint32_t wcta, uint32_t n_wctas, uint32
 
 // ---- manager side (one warp; lane q talks to rank q) ---------------------------------------------------------------
 
-__device__ __forceinline__ bool a_issue_and_wait(const ARank &R, AState *st, unsigned long long &seq, uint32_t type, unsigned long long &phases_run,
-                                                 bool wait) {
+__device__ __forceinline__ bool a_issue_and_wait(const ARank &R, AState *st, unsigned long long &seq, uint32_t type, int32_t k,
+                                                 unsigned long long &phases_run, bool wait) {
     ++seq;
-    if (lane_id() == 0) a_st_rel(&st->phase_word, (seq << 8) | type);
+    if (lane_id() == 0) a_st_rel(&st->phase_word, (seq << 40) | ((unsigned long long)type << 32) | (unsigned long long)(uint32_t)k);
     if (!wait) return true;
     ++phases_run;
     const unsigned long long want = phases_run * (unsigned long long)(R.ctas - 1u);
@@ -335,6 +358,7 @@ __device__ void a_manager(const ARank &R) {
     ACtl *mine = R.ctl_peer[R.rank];
     unsigned long long seq = 0, phases_run = 0, epoch = 0;
     int32_t prev_k = -1;
+    bool level_active = false;                // this rank processed entries in the level that just ended
     uint32_t n_alive = R.n_local, src = 2u;   // 2: every local unitig
     unsigned long long tp = a_ns();
 #define KG_APROF(slot)                                \
@@ -345,22 +369,32 @@ __device__ void a_manager(const ARank &R) {
     }
     bool failed = false;
     while (!failed) {
-        // ---- the smallest surviving degree on this rank
-        if (lane == 0) {
-            st->local_min = INT32_MAX;
-            st->n_alive = n_alive;
-            st->alive_src = src;
-            st->prev_k = prev_k;
+        // ---- a lower bound of the next level on this rank: the survivors' degrees as the last scan saw them and every
+        //      degree a decrement of this rank left above the level (a unitig that died since only makes the bound lower:
+        //      the level it names is then empty, which costs a scan, never a wrong answer).  Before the first level: a pass.
+        if (epoch == 0) {
+            if (lane == 0) {
+                st->local_min = INT32_MAX;
+                st->n_alive = n_alive;
+                st->alive_src = src;
+                st->prev_k = prev_k;
+            }
+            __syncwarp();
+            if (!a_issue_and_wait(R, st, seq, kPhMin, -1, phases_run, true)) { failed = true; break; }
         }
-        __syncwarp();
-        if (!a_issue_and_wait(R, st, seq, kPhMin, phases_run, true)) { failed = true; break; }
         KG_APROF(0);
         ++epoch;
         int32_t lmin = 0;
-        if (lane == 0) lmin = *(volatile int32_t *)&st->local_min;
+        if (lane == 0) {
+            lmin = *(volatile int32_t *)&st->local_min;
+            st->local_min = INT32_MAX;   // the coming scan and level collect the next bound
+        }
         lmin = __shfl_sync(kFullMask, lmin, 0);
-        if (has_peer) a_st_sys(&R.ctl_peer[lane]->min_next[R.rank], (epoch << 32) | (unsigned long long)(uint32_t)lmin);
+        // bit 31: this rank peeled something in the level that just ended (a level named by a stale bound can be empty everywhere)
+        const unsigned long long active_bit = level_active ? 0x80000000ull : 0ull;
+        if (has_peer) a_st_sys(&R.ctl_peer[lane]->min_next[R.rank], (epoch << 32) | active_bit | (unsigned long long)(uint32_t)lmin);
         int32_t gmin = INT32_MAX;
+        bool any_active = false;
         {
             const unsigned long long t0 = a_ns();
             uint32_t spins = 0;
@@ -370,10 +404,16 @@ __device__ void a_manager(const ARank &R) {
                 while (((w = a_ld_sys(&mine->min_next[lane])) >> 32) != epoch) {
                     if ((++spins & 1023u) == 0 && (*(volatile uint32_t *)&st->error || a_ns() - t0 > kAWatchdogNs)) { bad = true; break; }
                 }
-                gmin = (int32_t)(uint32_t)w;
+                gmin = (int32_t)((uint32_t)w & 0x7fffffffu);
+                any_active = ((uint32_t)w & 0x80000000u) != 0;
             }
             if (__ballot_sync(kFullMask, bad)) { if (lane == 0) atomicCAS(&st->error, 0u, 2u); failed = true; break; }
             gmin = warp_reduce_min(gmin);
+            any_active = __any_sync(kFullMask, any_active);
+        }
+        if (any_active && lane == 0) {   // the level that just ended peeled something somewhere: it counts
+            st->levels += 1;
+            st->max_core = prev_k;
         }
         KG_APROF(1);
         if (gmin == INT32_MAX) break;   // nothing alive anywhere
@@ -382,15 +422,13 @@ __device__ void a_manager(const ARank &R) {
         const uint32_t dst = src == 0u ? 1u : 0u;
         if (lane == 0) {
             st->cur_k = k;
-            st->alive_cnt[dst] = 0;
+            st->n_alive = n_alive;     // the list the scan reads (the survivors of the previous scan) ...
+            st->alive_src = src;
+            st->alive_cnt[dst] = 0;    // ... and the one it writes
         }
         __syncwarp();
-        if (!a_issue_and_wait(R, st, seq, kPhScan, phases_run, true)) { failed = true; break; }
-        if (lane == 0) {
-            n_alive = *(volatile uint32_t *)&st->alive_cnt[dst];
-            st->levels += 1;
-            st->max_core = k;
-        }
+        if (!a_issue_and_wait(R, st, seq, kPhScan, k, phases_run, true)) { failed = true; break; }
+        if (lane == 0) n_alive = *(volatile uint32_t *)&st->alive_cnt[dst];
         n_alive = __shfl_sync(kFullMask, n_alive, 0);
         src = dst;
         prev_k = k;
@@ -409,7 +447,9 @@ __device__ void a_manager(const ARank &R) {
             if (__ballot_sync(kFullMask, bad)) { if (lane == 0) atomicCAS(&st->error, 0u, 2u); failed = true; break; }
         }
         KG_APROF(3);
-        a_issue_and_wait(R, st, seq, kPhGo, phases_run, false);
+        a_issue_and_wait(R, st, seq, kPhGo, k, phases_run, false);
+        unsigned long long done_before = lane == 0 ? a_ld_sys(&mine->q_done) : 0ull;
+        done_before = __shfl_sync(kFullMask, done_before, 0);
         // ---- the end of the level: every rank idle at one instant
         {
             const unsigned long long t0 = a_ns();
@@ -429,11 +469,19 @@ __device__ void a_manager(const ARank &R) {
                     if (__any_sync(kFullMask, bad)) { if (lane == 0) atomicCAS(&st->error, 0u, 2u); failed = true; break; }
                 }
             }
+            unsigned long long done_after = lane == 0 ? a_ld_sys(&mine->q_done) : 0ull;
+            done_after = __shfl_sync(kFullMask, done_after, 0);
+            level_active = done_after != done_before;
+            if (lane == 0 && epoch <= (unsigned long long)kALvlProf) {
+                st->lvl_ns[epoch - 1] = (uint32_t)(a_ns() - t0);
+                st->lvl_k[epoch - 1] = k;
+                st->lvl_pushed[epoch - 1] = (uint32_t)(done_after - done_before);
+            }
         }
         KG_APROF(4);
     }
 #undef KG_APROF
-    a_issue_and_wait(R, st, seq, kPhExit, phases_run, false);
+    a_issue_and_wait(R, st, seq, kPhExit, -1, phases_run, false);
 }
 
 __global__ void __launch_bounds__(kAThreads, 2) apeel_kernel(const ARank *ranks, uint32_t ctas_per_rank) {
@@ -583,6 +631,11 @@ int dist_peel_async(kombgpu_dist_graph *g) {
                 "levels (go -> over) %.3f | peeled here %llu, slices %llu, entries visited %llu, remote decrements %llu, remote pushes %llu\n",
                 c->rank, fin.levels, ctas_per_rank, fin.prof_ns[0] * 1e-6, fin.prof_ns[1] * 1e-6, fin.prof_ns[2] * 1e-6, fin.prof_ns[3] * 1e-6,
                 fin.prof_ns[4] * 1e-6, peeled_here, fin.n_slices, fin.n_visited, fin.n_remote_dec, fin.n_remote_push);
+    if (getenv("KOMBGPU_DEBUG") && c->rank == 0) {
+        fprintf(stderr, "[kombgpu] apeel levels (k: us from go to over / entries processed on rank 0):");
+        for (uint32_t i = 0; i < fin.levels && i < (uint32_t)kALvlProf; ++i) fprintf(stderr, " %d:%.0f/%u", fin.lvl_k[i], fin.lvl_ns[i] * 1e-3, fin.lvl_pushed[i]);
+        fprintf(stderr, "\n");
+    }
     KG_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
     KG_CUDA(ctx, cudaEventSynchronize(ev1));
     cudaEventElapsedTime(&g->st.ms_peel, ev0, ev1);
