@@ -40,7 +40,7 @@ class DistStats(ctypes.Structure):
         ("max_degree", c_int32), ("max_coreness", c_int32), ("peel_levels", c_uint32), ("peel_subrounds", c_uint32),
         ("peel_solo_subrounds", c_uint32),
         ("ms_build", c_float), ("ms_peel", c_float), ("ms_corea", c_float),
-        ("ms_build_route", c_float), ("ms_build_sort", c_float), ("ms_build_csr", c_float),
+        ("ms_build_route", c_float), ("ms_build_sort", c_float), ("ms_build_csr", c_float), ("peel_async", c_uint32),
     ]
 
     def as_dict(self):

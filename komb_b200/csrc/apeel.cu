@@ -82,6 +82,7 @@ struct ARank {
     int32_t *deg_peer[kMaxRanks];
     unsigned long long *pool_peer[kMaxRanks];
     ACtl *ctl_peer[kMaxRanks];
+    uint8_t *dead_peer[kMaxRanks];             // every rank's map of peeled unitigs (global ids): written by the owners, read locally
     AState *st;
 };
 
@@ -119,6 +120,7 @@ __device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, 
     const uint32_t lane = lane_id();
     unsigned long long n_remote = 0, n_push = 0, n_own = 0;
     int32_t left = INT32_MAX;   // smallest degree above k this walk left behind
+    const uint8_t *dead = R.dead_peer[R.rank];
     for (uint32_t base = lo; base < hi; base += 32u * kAU) {
         uint32_t own[kAU], li[kAU];
         int32_t old[kAU];
@@ -128,8 +130,12 @@ __device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, 
             own[t] = 0xffffffffu;
             if (e < hi) {
                 const uint32_t u = R.col[e];
-                own[t] = u / R.step;
-                li[t] = u - own[t] * R.step;
+                // a unitig already peeled needs no decrement: its owner marked it in every rank's map when it peeled it (the
+                // mark may still be on its way: then the decrement is merely wasted)
+                if (!dead || !__ldcg(&dead[u])) {
+                    own[t] = u / R.step;
+                    li[t] = u - own[t] * R.step;
+                }
             }
         }
 #pragma unroll
@@ -185,6 +191,7 @@ __device__ __forceinline__ void a_process(const ARank &R, AState *st, unsigned l
     }
     const int32_t k = (int32_t)((entry >> 32) & 0x7fffffffu);
     if (lane == 0) R.core[v] = k;
+    if ((int)lane < R.world && R.dead_peer[lane]) R.dead_peer[lane][R.v_lo + v] = 1;   // lane q tells rank q
     uint32_t hi = row_hi;
     const uint32_t len = row_hi - row_lo;
     if (len > kASlice) {
@@ -295,7 +302,6 @@ __device__ void a_worker(const ARank &R, uint32_t wcta, uint32_t n_wctas, uint32
                 entry = a_ld_sys(pool + t);
                 // a slice only exists once its unitig's level was released; a unitig carries its level
                 if (entry != kAEmpty && ((entry & kASliceFlag) || (int32_t)((entry >> 32) & 0x7fffffffu) == go_k)) break;
-                if ((++spins & 3u) != 0) continue;
             }
             unsigned long long pw = *(volatile unsigned long long *)&st->phase_word;
             if ((pw >> 40) != seen) {
@@ -535,6 +541,16 @@ int dist_peel_async(kombgpu_dist_graph *g) {
     KG_TRY(sym_alloc(c, (size_t)g->step, &work, &work_peers));
     KG_TRY(sym_alloc(c, (size_t)cap64, &pool, &pool_peers));
     KG_TRY(sym_alloc(c, 1, &ctl, &ctl_peers));
+    // maps of peeled unitigs (skip decrements of neighbours that are gone): KOMBGPU_APEEL_DEADMAP=1.  Measured at N=2 on
+    // cfg2 the remote decrements halve (32.9 M -> 16.5 M per rank) and the peel gets 5 % SLOWER (the map lookup sits on the
+    // cascade's critical path and the decrements were not the bound), so it is off by default.
+    uint8_t *dead = nullptr;
+    PeerPtrs<uint8_t> dead_peers{};
+    const char *dm_env = getenv("KOMBGPU_APEEL_DEADMAP");
+    if (dm_env && dm_env[0] == '1') {
+        KG_TRY(sym_alloc(c, (size_t)g->n_global, &dead, &dead_peers));
+        KG_CUDA(ctx, cudaMemsetAsync(dead, 0, (size_t)(g->n_global ? g->n_global : 1), ctx->stream));
+    }
     KG_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(ACtl), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(pool, 0xff, (size_t)cap64 * sizeof(unsigned long long), ctx->stream));
     if (n_local) KG_CUDA(ctx, cudaMemcpyAsync(work, g->deg, (size_t)n_local * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -564,6 +580,7 @@ int dist_peel_async(kombgpu_dist_graph *g) {
         R.deg_peer[q] = work_peers.p[q];
         R.pool_peer[q] = pool_peers.p[q];
         R.ctl_peer[q] = ctl_peers.p[q];
+        R.dead_peer[q] = dead_peers.p[q];
     }
     R.st = state.p;
 
@@ -623,6 +640,7 @@ int dist_peel_async(kombgpu_dist_graph *g) {
     g->st.peel_levels = fin.levels;
     g->st.peel_subrounds = fin.levels;          // the ranks meet once per level here, not once per cascade generation
     g->st.peel_solo_subrounds = 0;
+    g->st.peel_async = 1;
     g->st.n_messages_sent = fin.n_remote_push;               // unitigs this rank discovered for other ranks (pushed into their pools)
     g->st.n_messages_recv = fin_ctl.q_tail - fin.n_own_push;   // unitigs other ranks pushed into this rank's pool
     g->has_core = true;

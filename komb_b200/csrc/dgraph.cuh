@@ -49,8 +49,9 @@ int route_keys(kombgpu_comm *c, const uint64_t *keys, uint64_t n, uint32_t step,
 int dist_peel(kombgpu_dist_graph *g);
 // apeel.cu
 int dist_peel_async(kombgpu_dist_graph *g);
-// which peel a build prepares for: KOMBGPU_DIST_PEEL=log (ranks meet once per cascade generation, ppeel.cu) or async (default)
-bool dist_peel_is_async();
+// which peel a build prepares for (pbuild.cu): KOMBGPU_DIST_PEEL = log (ranks meet once per cascade generation, ppeel.cu),
+// async (apeel.cu) or auto (default: by the largest degree).  0 log, 1 async, 2 auto.
+int dist_peel_mode();
 // pcorea.cu
 int dist_corea(kombgpu_dist_graph *g, int key_mode);
 

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) swap_edges_kernel(const uint64_t *__
 // by_row: the keys are (u - v_lo) << 32 | neighbour instead (the rank's rows, for the asynchronous peel)
 __global__ void __launch_bounds__(kThreads) nbr_keys_kernel(const uint64_t *__restrict__ edges, uint64_t n_fwd, const uint64_t *__restrict__ back,
                                                             uint64_t n_back, uint32_t v_lo, uint32_t n_local, uint32_t n_global, bool by_row,
-                                                            uint64_t *__restrict__ keys, int32_t *__restrict__ back_cnt, uint32_t *__restrict__ err) {
+                                                            uint64_t *__restrict__ keys, uint32_t *__restrict__ err) {
     const uint64_t total = n_fwd + n_back;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t u, w;
@@ -149,13 +149,23 @@ __global__ void __launch_bounds__(kThreads) nbr_keys_kernel(const uint64_t *__re
             u = (uint32_t)(s >> 32);
             w = (uint32_t)s;
             if (u >= n_local || w >= n_global) { atomicExch(err, 2u); keys[i] = 0; continue; }   // a mis-routed entry must not write past the arrays
-            atomicAdd(&back_cnt[u], 1);
         }
         keys[i] = by_row ? (((uint64_t)u << 32) | w) : (((uint64_t)w << 32) | u);
     }
 }
 
-// deg[u] = forward neighbours (from the forward index) + backward neighbours (counted by nbr_keys_kernel)
+// back_cnt[u] += 1 for every arrival ((u - v_lo) << 32 | w): the backward neighbours of the local unitigs
+__global__ void __launch_bounds__(kThreads) back_count_kernel(const uint64_t *__restrict__ back, uint64_t n_back, uint32_t n_local, uint32_t n_global,
+                                                              int32_t *__restrict__ back_cnt, uint32_t *__restrict__ err) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_back; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = back[i];
+        const uint32_t u = (uint32_t)(s >> 32), w = (uint32_t)s;
+        if (u >= n_local || w >= n_global) { atomicExch(err, 2u); continue; }
+        atomicAdd(&back_cnt[u], 1);
+    }
+}
+
+// deg[u] = forward neighbours (from the forward index) + backward neighbours (counted by back_count_kernel)
 __global__ void __launch_bounds__(kThreads) pdegree_kernel(const uint32_t *__restrict__ fwd_start, uint32_t n_local, int32_t *__restrict__ deg,
                                                            int32_t *__restrict__ max_deg) {
     int32_t m = 0;
@@ -189,9 +199,17 @@ struct EvTimer {   // CUDA-event split timer on the context's stream
 
 }  // namespace
 
-bool dist_peel_is_async() {
+// KOMBGPU_DIST_PEEL = async | log | auto (default).  The asynchronous peel (apeel.cu) decrements a neighbour where it
+// lives, with an atomic over NVLink: a hub unitig takes one remote atomic per neighbour, all on one address, and those
+// serialise at its home L2 (measured on 8 GPUs: cfg3, R-MAT with hubs of 10^5 .. 6 x 10^5 neighbours, 85 ms against 52 ms
+// for the log-based peel; cfg2 x 8, largest hub 1.7 x 10^5, 13.0 against 14.4 ms; a 1/8 share of cfg4, degrees <= 55, 6.7
+// against 14.7 ms).  auto: asynchronous unless the largest degree of the graph exceeds kAsyncMaxDegree.
+constexpr int32_t kAsyncMaxDegree = 1 << 18;
+int dist_peel_mode() {   // 0 log, 1 async, 2 auto
     const char *e = getenv("KOMBGPU_DIST_PEEL");
-    return !(e && e[0] == 'l');
+    if (e && e[0] == 'l') return 0;
+    if (e && e[0] == 'a' && e[1] == 's') return 1;
+    return 2;
 }
 
 int route_keys(kombgpu_comm *c, const uint64_t *keys, uint64_t n, uint32_t step, bool rebase, uint64_t **recv, uint64_t *n_recv) {
@@ -336,12 +354,25 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
     KG_CUDA(ctx, cudaMemsetAsync(deg.p, 0, (size_t)(n_local ? n_local : 1) * sizeof(int32_t), ctx->stream));
     KG_TRY(row_starts(ctx, edges.p, n_fwd, g->v_lo, n_local, n_global, fwd_start.p, d_err.p));
-    const bool by_row = dist_peel_is_async();
-    if (n_dir)
-        KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
-                  n_global, by_row, keys_a.p, deg.p, d_err.p);
+    // degrees first (forward index + a count of the arrivals): the largest one picks the peel, the peel picks the layout
+    if (n_back)
+        KG_LAUNCH(ctx, back_count_kernel, min(grid_for(n_back, kThreads), 148u * 16u), kThreads, 0, back, n_back, n_local, n_global, deg.p,
+                  d_err.p);
     if (n_local)
         KG_LAUNCH(ctx, pdegree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, fwd_start.p, n_local, deg.p, max_deg.p);
+    bool by_row = dist_peel_mode() == 1;
+    if (dist_peel_mode() == 2) {   // the layout follows the peel, the peel follows the largest degree of the whole graph
+        int32_t h_max_now = 0;
+        KG_TRY(read_back(ctx, max_deg.p, &h_max_now, 1));
+        unsigned long long mine_max = (unsigned long long)(uint32_t)h_max_now, all_max[kMaxRanks];
+        KG_TRY(comm_exchange(c, &mine_max, 1, all_max));
+        int32_t gmax_now = 0;
+        for (int q = 0; q < world; ++q) gmax_now = max(gmax_now, (int32_t)all_max[q]);
+        by_row = gmax_now <= kAsyncMaxDegree;
+    }
+    if (n_dir)
+        KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
+                  n_global, by_row, keys_a.p, d_err.p);
     uint64_t *nsorted = keys_a.p;
     {
         RadixPass passes[8];
