@@ -116,11 +116,11 @@ __device__ __forceinline__ int32_t a_ld_deg(const int32_t *p) {
 // ---- worker side ------------------------------------------------------------------------------------------------
 
 // decrement the neighbours col[lo, hi) of a unitig peeled at level k (whole warp)
-__device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, uint32_t hi, int32_t k) {
+__device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, uint32_t hi, int32_t k, bool use_map) {
     const uint32_t lane = lane_id();
     unsigned long long n_remote = 0, n_push = 0, n_own = 0;
     int32_t left = INT32_MAX;   // smallest degree above k this walk left behind
-    const uint8_t *dead = R.dead_peer[R.rank];
+    const uint8_t *dead = use_map ? R.dead_peer[R.rank] : nullptr;
     for (uint32_t base = lo; base < hi; base += 32u * kAU) {
         uint32_t own[kAU], li[kAU];
         int32_t old[kAU];
@@ -177,8 +177,16 @@ __device__ __forceinline__ void a_walk(const ARank &R, AState *st, uint32_t lo, 
     }
 }
 
-__device__ __forceinline__ void a_process(const ARank &R, AState *st, unsigned long long entry) {
+// The map of peeled unitigs saves the decrements of neighbours that are gone (half of all decrements), but looking a
+// neighbour up before decrementing it adds a load to a cascade's critical path.  So it is consulted only while the pool
+// holds a backlog (the level is bound by the rate of decrements, not by the length of a chain): measured on 8 GPUs with
+// cfg2 x 8, always on: the last level 4.9 -> 3.1 ms, the level before it (277 dependent generations) 3.6 -> 4.0 ms.
+constexpr unsigned long long kABacklog = 4096;
+
+__device__ __forceinline__ void a_process(const ARank &R, AState *st, unsigned long long entry, unsigned long long ticket) {
     const uint32_t lane = lane_id();
+    const bool use_map = R.dead_peer[R.rank] != nullptr &&
+                         *(volatile unsigned long long *)&R.ctl_peer[R.rank]->q_tail > ticket + kABacklog;
     const uint32_t v = (uint32_t)entry;
     if (v >= R.n_local) { atomicCAS(&st->error, 0u, 4u); return; }
     const uint32_t row_lo = R.row_ptr[v], row_hi = R.row_ptr[v + 1];
@@ -186,7 +194,7 @@ __device__ __forceinline__ void a_process(const ARank &R, AState *st, unsigned l
         const uint32_t piece = (uint32_t)(entry >> 32) & 0x1fffffu;
         const int32_t k = *(volatile int32_t *)&st->cur_k;   // slices are made and walked inside one level, on this rank
         const uint32_t lo = row_lo + piece * kASlice;
-        a_walk(R, st, lo, min(lo + kASlice, row_hi), k);
+        a_walk(R, st, lo, min(lo + kASlice, row_hi), k, use_map);
         return;
     }
     const int32_t k = (int32_t)((entry >> 32) & 0x7fffffffu);
@@ -209,7 +217,7 @@ __device__ __forceinline__ void a_process(const ARank &R, AState *st, unsigned l
         }
         hi = row_lo + kASlice;
     }
-    a_walk(R, st, row_lo, hi, k);
+    a_walk(R, st, row_lo, hi, k, use_map);
 }
 
 // MIN phase (all threads of a worker CTA): the smallest degree above prev_k among the listed unitigs
@@ -332,7 +340,7 @@ __device__ void a_worker(const ARank &R, uint32_t wcta, uint32_t n_wctas, uint32
                 if (a_ns() - t0 > kAWatchdogNs) { atomicCAS(&st->error, 0u, 1u); return; }
             }
         }
-        a_process(R, st, entry);
+        a_process(R, st, entry, t);
     }
 }
 
@@ -541,13 +549,11 @@ int dist_peel_async(kombgpu_dist_graph *g) {
     KG_TRY(sym_alloc(c, (size_t)g->step, &work, &work_peers));
     KG_TRY(sym_alloc(c, (size_t)cap64, &pool, &pool_peers));
     KG_TRY(sym_alloc(c, 1, &ctl, &ctl_peers));
-    // maps of peeled unitigs (skip decrements of neighbours that are gone): KOMBGPU_APEEL_DEADMAP=1.  Measured at N=2 on
-    // cfg2 the remote decrements halve (32.9 M -> 16.5 M per rank) and the peel gets 5 % SLOWER (the map lookup sits on the
-    // cascade's critical path and the decrements were not the bound), so it is off by default.
+    // maps of peeled unitigs (one byte per unitig of the graph on every rank; KOMBGPU_APEEL_DEADMAP=0 turns them off)
     uint8_t *dead = nullptr;
     PeerPtrs<uint8_t> dead_peers{};
     const char *dm_env = getenv("KOMBGPU_APEEL_DEADMAP");
-    if (dm_env && dm_env[0] == '1') {
+    if (!(dm_env && dm_env[0] == '0')) {
         KG_TRY(sym_alloc(c, (size_t)g->n_global, &dead, &dead_peers));
         KG_CUDA(ctx, cudaMemsetAsync(dead, 0, (size_t)(g->n_global ? g->n_global : 1), ctx->stream));
     }
