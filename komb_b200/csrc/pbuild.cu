@@ -203,8 +203,13 @@ struct EvTimer {   // CUDA-event split timer on the context's stream
 // lives, with an atomic over NVLink: a hub unitig takes one remote atomic per neighbour, all on one address, and those
 // serialise at its home L2 (measured on 8 GPUs: cfg3, R-MAT with hubs of 10^5 .. 6 x 10^5 neighbours, 85 ms against 52 ms
 // for the log-based peel; cfg2 x 8, largest hub 1.7 x 10^5, 13.0 against 14.4 ms; a 1/8 share of cfg4, degrees <= 55, 6.7
-// against 14.7 ms).  auto: asynchronous unless the largest degree of the graph exceeds kAsyncMaxDegree.
+// against 14.7 ms).  Its walk is also the simpler, slower one per entry (a system-scope atomic and an owner lookup per
+// neighbour): cfg4 at full size, 243 M adjacency entries per rank and only 28 levels, takes it 42.9 ms against 23.9 ms;
+// a 1/8 share of cfg4 on 2 GPUs (122 M entries per rank) 22.1 against 15.0 ms; cfg2 (66 M per rank) 9.2 against 11.1 ms.
+// auto: asynchronous unless the largest degree of the graph exceeds kAsyncMaxDegree or a rank holds more than
+// kAsyncMaxEntries adjacency entries (the peel is then bound by the rate of decrements, not by the length of its chains).
 constexpr int32_t kAsyncMaxDegree = 1 << 18;
+constexpr unsigned long long kAsyncMaxEntries = 96ull << 20;
 int dist_peel_mode() {   // 0 log, 1 async, 2 auto
     const char *e = getenv("KOMBGPU_DIST_PEEL");
     if (e && e[0] == 'l') return 0;
@@ -361,14 +366,18 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
     if (n_local)
         KG_LAUNCH(ctx, pdegree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, fwd_start.p, n_local, deg.p, max_deg.p);
     bool by_row = dist_peel_mode() == 1;
-    if (dist_peel_mode() == 2) {   // the layout follows the peel, the peel follows the largest degree of the whole graph
+    if (dist_peel_mode() == 2) {   // the layout follows the peel, the peel follows the shape of the whole graph
         int32_t h_max_now = 0;
         KG_TRY(read_back(ctx, max_deg.p, &h_max_now, 1));
-        unsigned long long mine_max = (unsigned long long)(uint32_t)h_max_now, all_max[kMaxRanks];
-        KG_TRY(comm_exchange(c, &mine_max, 1, all_max));
+        unsigned long long mine_shape[2] = {(unsigned long long)(uint32_t)h_max_now, (unsigned long long)n_dir}, all_shape[kMaxRanks * 2];
+        KG_TRY(comm_exchange(c, mine_shape, 2, all_shape));
         int32_t gmax_now = 0;
-        for (int q = 0; q < world; ++q) gmax_now = max(gmax_now, (int32_t)all_max[q]);
-        by_row = gmax_now <= kAsyncMaxDegree;
+        unsigned long long dir_max = 0;
+        for (int q = 0; q < world; ++q) {
+            gmax_now = max(gmax_now, (int32_t)all_shape[q * 2]);
+            dir_max = all_shape[q * 2 + 1] > dir_max ? all_shape[q * 2 + 1] : dir_max;
+        }
+        by_row = gmax_now <= kAsyncMaxDegree && dir_max <= kAsyncMaxEntries;
     }
     if (n_dir)
         KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
