@@ -37,6 +37,9 @@ METRIC = "hot-path hits/s (graph build + k-core peel + CORE-A), with peel edges/
 DTYPE = "u32/u64 ids, f64 scores"
 
 
+PEEL_KINDS = {0: "log", 1: "async", 2: "replicated"}
+
+
 def workload_config(world: int) -> dict:
     """The `config` object: identical for our arm and the reference arm (the driver compares them)."""
     return {"workload": "cfg2: synthetic metagenome unitig graph, 1M unitigs, 5M read pairs (~20M hits) per GPU"
@@ -793,17 +796,20 @@ def run_ours_multi(args, rank, world, local_rank):
                            "directed_entries_per_rank": [int(x) for x in tot[:, 4]]},
         "parallelism": f"unitig-range partition x{world}, one process per GPU; peer-memory path of libkombgpu: pairs routed to the owner "
                        "of min(u,v) by stores into peer memory; device-driven peel, one persistent kernel per GPU ("
-                       + ("asynchronous: a neighbour is decremented where it lives by an atomic over NVLink, a unitig that falls to the "
-                          "level is pushed into its owner's pool, ranks meet once per level" if st.get("peel_async") else
-                          "log-based: ranks broadcast the unitigs they peel and meet once per cascade generation through flags in peer memory")
-                       + "; chosen by the largest degree, KOMBGPU_DIST_PEEL overrides), sharded CORE-A; no collective library on the data "
+                       + {1: "asynchronous: a neighbour is decremented where it lives by an atomic over NVLink, a unitig that falls to the "
+                             "level is pushed into its owner's pool, ranks meet once per level",
+                          2: "replicated: the graph is small, every rank pulls the other ranks' rows out of peer memory and peels the whole "
+                             "graph with the single-GPU kernel",
+                          0: "log-based: ranks broadcast the unitigs they peel and meet once per cascade generation through flags in peer "
+                             "memory"}[int(st.get("peel_async", 0))]
+                       + "; chosen by the shape of the graph, KOMBGPU_DIST_PEEL overrides), sharded CORE-A; no collective library on the data "
                        "path (torch.distributed only bootstraps the cudaIpc handles)",
         "stages": {"build": {"ms": ms_build, "hits_per_s": H / (ms_build * 1e-3), "algorithmic_bytes": b_build,
                              "frac_hbm": b_build / (ms_build * 1e-3) / 1e9 / (hbm_gbs * world),
                              "route_ms": ms_route, "sort_unique_ms": ms_sort, "csr_ms": ms_csr},
                    "peel": {"ms": ms_peel, "edges_per_s": E / (ms_peel * 1e-3), "algorithmic_bytes": b_peel,
                             "frac_hbm": b_peel / (ms_peel * 1e-3) / 1e9 / (hbm_gbs * world),
-                            "kind": "async" if st.get("peel_async") else "log",
+                            "kind": PEEL_KINDS[int(st.get("peel_async", 0))],
                             "subrounds": st["peel_subrounds"], "solo_subrounds_rank0": st["peel_solo_subrounds"],
                             "messages": msgs, "message_bytes_over_nvlink": 4 * msgs},
                    "corea": {"ms": ms_corea, "vertices_per_s": n / (ms_corea * 1e-3)},
@@ -811,7 +817,8 @@ def run_ours_multi(args, rank, world, local_rank):
                                         "peel replicated on every GPU (the default of round 1), same input"}},
         "peel_edges_per_s": E / (ms_peel * 1e-3),
         "build_hits_per_s": H / (ms_build * 1e-3),
-        "roofline": {"kernel": ("apeel_kernel (asynchronous partitioned peel" if st.get("peel_async") else "ppeel_kernel (log-based partitioned peel")
+        "roofline": {"kernel": {1: "apeel_kernel (asynchronous partitioned peel", 0: "ppeel_kernel (log-based partitioned peel",
+                                2: "peel_kernel (replicated peel of the gathered graph"}[int(st.get("peel_async", 0))]
                      + ", one persistent kernel per GPU)", "bound": "hbm",
                      "achieved": b_peel / (ms_peel * 1e-3) / 1e9, "peak": hbm_gbs * world, "unit": "GB/s",
                      "frac": b_peel / (ms_peel * 1e-3) / 1e9 / (hbm_gbs * world), "traffic": None,
@@ -891,7 +898,7 @@ def run_config_multi(ctx, comm, tcomm, name, world, rank, hbm_gbs, timed, reps: 
                                   st["n_messages_sent"]])
     out = {"workload": desc, "n_gpus": world, "n_unitigs": n, "n_inputs": int(sums[:, 2].sum()), "n_pairs": int(sums[:, 3].sum()), "n_edges": E,
            "max_degree": st["max_degree"], "max_coreness": st["max_coreness"], "peel_levels": st["peel_levels"],
-           "peel_kind": "async" if st.get("peel_async") else "log",
+           "peel_kind": PEEL_KINDS[int(st.get("peel_async", 0))],
            "peel_subrounds": st["peel_subrounds"], "peel_messages": int(sums[:, 4].sum()),
            "ms_total_max_over_ranks": best_t, "ms_build": best["ms_build"], "ms_peel": best["ms_peel"], "ms_corea": best["ms_corea"],
            "edges_per_s_total": E / (best_t * 1e-3), "peel_edges_per_s": E / (best["ms_peel"] * 1e-3),

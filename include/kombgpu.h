@@ -424,7 +424,8 @@ typedef struct kombgpu_dist_stats {
     uint32_t peel_solo_subrounds; /* of those, walked by one CTA on this GPU (thin cascades)    */
     float ms_build, ms_peel, ms_corea;   /* CUDA-event times on this rank                       */
     float ms_build_route, ms_build_sort, ms_build_csr;
-    uint32_t peel_async;        /* 1: the asynchronous peel ran (ranks meet once per level), 0: the log-based one */
+    uint32_t peel_async;        /* which peel ran: 0 log-based (ranks meet once per cascade generation), 1 asynchronous
+                                   (ranks meet once per level), 2 replicated (small graph: every rank peels all of it) */
 } kombgpu_dist_stats;
 
 /* Stage 1..3 over all ranks, collective.  Inputs are device pointers on the rank's device: the hits of THIS

@@ -38,7 +38,7 @@ constexpr int kAThreads = 512;
 constexpr int kAWarps = kAThreads / 32;
 constexpr int kAU = 4;                        // independent decrement chains per lane
 constexpr uint32_t kASlice = 2048;            // rows longer than this are cut into slices of this many entries
-constexpr int kAScanItems = 4;
+constexpr int kAScanItems = 8;
 constexpr unsigned long long kAEmpty = ~0ull;
 constexpr unsigned long long kASliceFlag = 1ull << 63;   // entry = flag | piece << 32 | local id ; else k << 32 | local id
 constexpr unsigned long long kAWatchdogNs = 20ull * 1000000000ull;
@@ -107,12 +107,6 @@ __device__ __forceinline__ unsigned long long a_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ int32_t a_ld_deg(const int32_t *p) {
-    int32_t v;
-    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // ---- worker side ------------------------------------------------------------------------------------------------
 
 // decrement the neighbours col[lo, hi) of a unitig peeled at level k (whole warp)

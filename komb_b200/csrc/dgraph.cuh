@@ -27,6 +27,7 @@ struct kombgpu_dist_graph {
     // ids of the neighbours of local unitig u (rows need no order inside).  A build makes one of the two layouts.
     uint32_t *row_ptr32 = nullptr; // [n_local + 1]
     uint32_t *col = nullptr;       // [n_directed]
+    int peel_choice = 0;           // what the build prepared for: 0 log-based (ppeel.cu), 1 asynchronous (apeel.cu), 2 replicated (rpeel.cu)
     int32_t *deg = nullptr;        // [n_local]
     int32_t *core = nullptr;       // [n_local] after the peel
     double *score = nullptr;       // [n_local] after CORE-A
@@ -49,8 +50,10 @@ int route_keys(kombgpu_comm *c, const uint64_t *keys, uint64_t n, uint32_t step,
 int dist_peel(kombgpu_dist_graph *g);
 // apeel.cu
 int dist_peel_async(kombgpu_dist_graph *g);
+// rpeel.cu
+int dist_peel_replicated(kombgpu_dist_graph *g);
 // which peel a build prepares for (pbuild.cu): KOMBGPU_DIST_PEEL = log (ranks meet once per cascade generation, ppeel.cu),
-// async (apeel.cu) or auto (default: by the largest degree).  0 log, 1 async, 2 auto.
+// async (apeel.cu), replicated (rpeel.cu) or auto (default: by the shape of the graph).  0 log, 1 async, 2 auto, 3 replicated.
 int dist_peel_mode();
 // pcorea.cu
 int dist_corea(kombgpu_dist_graph *g, int key_mode);

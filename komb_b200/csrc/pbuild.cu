@@ -210,10 +210,14 @@ struct EvTimer {   // CUDA-event split timer on the context's stream
 // kAsyncMaxEntries adjacency entries (the peel is then bound by the rate of decrements, not by the length of its chains).
 constexpr int32_t kAsyncMaxDegree = 1 << 18;
 constexpr unsigned long long kAsyncMaxEntries = 96ull << 20;
-int dist_peel_mode() {   // 0 log, 1 async, 2 auto
+// A graph small enough for one GPU to peel in a few milliseconds is not partitioned for the peel at all (rpeel.cu): every
+// rank pulls the other ranks' rows and runs the single-GPU kernel (cfg2 x 2 / x 4: 5.5 / 8.4 ms against 9.3 / 18.6 ms).
+constexpr unsigned long long kReplicateMaxEntries = 300ull << 20;   // adjacency entries of the whole graph
+int dist_peel_mode() {   // 0 log, 1 async, 2 auto, 3 replicated
     const char *e = getenv("KOMBGPU_DIST_PEEL");
     if (e && e[0] == 'l') return 0;
     if (e && e[0] == 'a' && e[1] == 's') return 1;
+    if (e && e[0] == 'r') return 3;
     return 2;
 }
 
@@ -365,20 +369,24 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
                   d_err.p);
     if (n_local)
         KG_LAUNCH(ctx, pdegree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, fwd_start.p, n_local, deg.p, max_deg.p);
-    bool by_row = dist_peel_mode() == 1;
+    int choice = dist_peel_mode() == 2 ? 0 : (dist_peel_mode() == 3 ? 2 : dist_peel_mode());
     if (dist_peel_mode() == 2) {   // the layout follows the peel, the peel follows the shape of the whole graph
         int32_t h_max_now = 0;
         KG_TRY(read_back(ctx, max_deg.p, &h_max_now, 1));
         unsigned long long mine_shape[2] = {(unsigned long long)(uint32_t)h_max_now, (unsigned long long)n_dir}, all_shape[kMaxRanks * 2];
         KG_TRY(comm_exchange(c, mine_shape, 2, all_shape));
         int32_t gmax_now = 0;
-        unsigned long long dir_max = 0;
+        unsigned long long dir_max = 0, dir_total = 0;
         for (int q = 0; q < world; ++q) {
             gmax_now = max(gmax_now, (int32_t)all_shape[q * 2]);
             dir_max = all_shape[q * 2 + 1] > dir_max ? all_shape[q * 2 + 1] : dir_max;
+            dir_total += all_shape[q * 2 + 1];
         }
-        by_row = gmax_now <= kAsyncMaxDegree && dir_max <= kAsyncMaxEntries;
+        if (world > 1 && dir_total <= kReplicateMaxEntries) choice = 2;
+        else choice = (gmax_now <= kAsyncMaxDegree && dir_max <= kAsyncMaxEntries) ? 1 : 0;
     }
+    const bool by_row = choice != 0;
+    g->peel_choice = choice;
     if (n_dir)
         KG_LAUNCH(ctx, nbr_keys_kernel, min(grid_for(n_dir, kThreads), 148u * 16u), kThreads, 0, edges.p, n_fwd, back, n_back, g->v_lo, n_local,
                   n_global, by_row, keys_a.p, d_err.p);

@@ -93,7 +93,8 @@ int kombgpu_dist_coreness(kombgpu_dist_graph *g) {
     if (!g) return KOMBGPU_EINVAL;
     KG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
     if (g->has_core) return KOMBGPU_OK;
-    return g->row_ptr32 ? dist_peel_async(g) : dist_peel(g);   // the layout the build made decides (KOMBGPU_DIST_PEEL)
+    // what the build prepared for (KOMBGPU_DIST_PEEL, or the shape of the graph)
+    return g->peel_choice == 2 ? dist_peel_replicated(g) : (g->peel_choice == 1 ? dist_peel_async(g) : dist_peel(g));
 }
 
 int kombgpu_dist_corea(kombgpu_dist_graph *g, int key_mode) {

@@ -112,12 +112,13 @@ def _check(oracle, parts, case, key_mode):
     return parts
 
 
-@pytest.mark.parametrize("peel", ["async", "log"])
+@pytest.mark.parametrize("peel", ["async", "log", "replicated", "auto"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("case", ["hits_small", "hits_mid", "rmat", "ramp", "hubs", "empty"])
 def test_peer_path_emulated_ranks(oracle_mod, monkeypatch, case, world, peel):
     """peel: the asynchronous peel (apeel.cu: remote atomics on the owners' degrees, discoveries pushed into the owners'
-    pools, ranks meet once per level) or the log-based one (ppeel.cu: ranks meet once per cascade generation)."""
+    pools, ranks meet once per level), the log-based one (ppeel.cu: ranks meet once per cascade generation), the
+    replicated one (rpeel.cu: every rank pulls the others' rows and peels the whole graph), or the library's choice."""
     from komb_b200.peer import run_local
     monkeypatch.setenv("KOMBGPU_DIST_PEEL", peel)
     key_mode = oracle_mod.KEY_EXACT64 if case in ("rmat", "ramp") else oracle_mod.KEY_REF32
@@ -125,7 +126,9 @@ def test_peer_path_emulated_ranks(oracle_mod, monkeypatch, case, world, peel):
     parts = _check(oracle_mod, parts, case, key_mode)
     if world > 1:
         assert all(p["same_device"] for p in parts)
-        if case in ("hits_mid", "rmat", "hubs"):
+        kinds = {p["stats"]["peel_async"] for p in parts}
+        assert kinds == {{"log": 0, "async": 1, "replicated": 2, "auto": 2}[peel]}      # small graphs: auto replicates
+        if case in ("hits_mid", "rmat", "hubs") and peel in ("async", "log"):
             assert sum(p["stats"]["n_messages_sent"] for p in parts) == sum(p["stats"]["n_messages_recv"] for p in parts) > 0
     if case == "hits_small":      # multiplicities survive the routing: their sum is the number of pairs emitted
         assert sum(int(p["mult"].sum()) for p in parts) == sum(p["stats"]["n_pairs_local"] for p in parts)
@@ -148,11 +151,13 @@ def test_peer_path_bad_input_fails_on_every_rank():
     assert run_local(2, body) == [-1, -1]
 
 
+@pytest.mark.parametrize("peel", ["async", "log", "replicated"])
 @pytest.mark.parametrize("case", ["hits_mid", "rmat", "ramp", "hubs"])
-def test_peer_path_one_gpu_per_rank_threads(oracle_mod, case):
+def test_peer_path_one_gpu_per_rank_threads(oracle_mod, monkeypatch, case, peel):
     """Real peer access: one GPU per rank, ranks are threads of this process (what a C++ host like komb2 does)."""
     import torch
     from komb_b200.peer import run_local
+    monkeypatch.setenv("KOMBGPU_DIST_PEEL", peel)
     n_dev = torch.cuda.device_count()
     if n_dev < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -184,8 +189,9 @@ def _proc_worker(rank, world, port, out_dir, case, key_mode):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peel", ["async", "log", "replicated"])
 @pytest.mark.parametrize("case", ["hits_mid", "rmat"])
-def test_peer_path_one_process_per_gpu_nccl_bootstrap(tmp_path, oracle_mod, case):
+def test_peer_path_one_process_per_gpu_nccl_bootstrap(tmp_path, oracle_mod, monkeypatch, case, peel):
     """The bench's arrangement: one process per GPU, symmetric heap mapped with cudaIpc, bootstrap all-gather
     over torch.distributed with the NCCL backend."""
     import torch
@@ -194,6 +200,7 @@ def test_peer_path_one_process_per_gpu_nccl_bootstrap(tmp_path, oracle_mod, case
     if n_dev < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
+    monkeypatch.setenv("KOMBGPU_DIST_PEEL", peel)      # inherited by the spawned ranks
     key_mode = oracle_mod.KEY_EXACT64 if case == "rmat" else oracle_mod.KEY_REF32
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_proc_worker, args=(world, port, str(tmp_path), case, key_mode), nprocs=world, join=True)
