@@ -211,8 +211,11 @@ struct EvTimer {   // CUDA-event split timer on the context's stream
 constexpr int32_t kAsyncMaxDegree = 1 << 18;
 constexpr unsigned long long kAsyncMaxEntries = 96ull << 20;
 // A graph small enough for one GPU to peel in a few milliseconds is not partitioned for the peel at all (rpeel.cu): every
-// rank pulls the other ranks' rows and runs the single-GPU kernel (cfg2 x 2 / x 4: 5.5 / 8.4 ms against 9.3 / 18.6 ms).
+// rank pulls the other ranks' rows and runs the single-GPU kernel (cfg2 x 2 / x 4: 4.4 / 10.9 ms against 9.3 / 18.6 ms).
+// Not beyond four ranks: on 8 GPUs the pull and the peel of the whole graph cost more than the partitioned peel's hops
+// (cfg2 x 8: 21.5 against 12.7 ms; a 1/8 share of cfg4: 11.2 against 7.9 ms).
 constexpr unsigned long long kReplicateMaxEntries = 300ull << 20;   // adjacency entries of the whole graph
+constexpr int kReplicateMaxWorld = 4;
 int dist_peel_mode() {   // 0 log, 1 async, 2 auto, 3 replicated
     const char *e = getenv("KOMBGPU_DIST_PEEL");
     if (e && e[0] == 'l') return 0;
@@ -382,7 +385,7 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
             dir_max = all_shape[q * 2 + 1] > dir_max ? all_shape[q * 2 + 1] : dir_max;
             dir_total += all_shape[q * 2 + 1];
         }
-        if (world > 1 && dir_total <= kReplicateMaxEntries) choice = 2;
+        if (world > 1 && world <= kReplicateMaxWorld && dir_total <= kReplicateMaxEntries) choice = 2;
         else choice = (gmax_now <= kAsyncMaxDegree && dir_max <= kAsyncMaxEntries) ? 1 : 0;
     }
     const bool by_row = choice != 0;
