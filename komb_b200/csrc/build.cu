@@ -397,11 +397,22 @@ __global__ void lower_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t 
 }
 
 // row r of a partition owns the keys whose high word is base + r
+// *err is raised when a key's row lies outside [base, base + n_rows) or its low word is >= lo_bound (an entry routed to
+// the wrong rank, or a corrupt one, must not write past the arrays)
 __global__ void __launch_bounds__(kThreads) row_bounds_base_kernel(const uint64_t *__restrict__ keys, uint64_t count,
-                                                                   uint32_t base, uint32_t n_rows, uint64_t *__restrict__ start) {
+                                                                   uint32_t base, uint32_t n_rows, uint32_t lo_bound,
+                                                                   uint64_t *__restrict__ start, uint32_t *__restrict__ err) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += (uint64_t)gridDim.x * blockDim.x) {
-        int64_t cur = i < count ? (int64_t)(keys[i] >> 32) - (int64_t)base : (int64_t)n_rows;
-        int64_t prev = i > 0 ? (int64_t)(keys[i - 1] >> 32) - (int64_t)base : -1;
+        int64_t cur = (int64_t)n_rows, prev = -1;
+        if (i < count) {
+            const uint64_t k = keys[i];
+            cur = (int64_t)(uint32_t)(k >> 32) - (int64_t)base;
+            if (cur < 0 || cur >= (int64_t)n_rows || (uint32_t)k >= lo_bound) { atomicExch(err, 2u); cur = (int64_t)n_rows; }
+        }
+        if (i > 0) {
+            prev = (int64_t)(uint32_t)(keys[i - 1] >> 32) - (int64_t)base;
+            if (prev < 0 || prev >= (int64_t)n_rows) prev = (int64_t)n_rows;
+        }
         for (int64_t x = prev + 1; x <= cur; ++x) start[x] = i;
     }
 }
@@ -740,8 +751,14 @@ int csr_from_directed(kombgpu_ctx *ctx, const uint64_t *entries, uint64_t count,
     KG_ALLOC(ctx, deg, n_local);
     if (!max_deg) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
     KG_CUDA(ctx, cudaMemsetAsync(max_deg.p, 0, sizeof(int32_t), ctx->stream));
+    DevBuf<uint32_t> d_err(ctx, 1);
+    if (!d_err) return ctx_fail(ctx, KOMBGPU_ENOMEM, "workspace");
+    KG_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), ctx->stream));
     KG_LAUNCH(ctx, row_bounds_base_kernel, min(grid_for(nd + 1, kThreads), 148u * 16u), kThreads, 0, uniq.p, nd, v_lo, n_local,
-              row_ptr.p);
+              n_global ? n_global : 1u, row_ptr.p, d_err.p);
+    uint32_t h_err = 0;
+    KG_TRY(read_back(ctx, d_err.p, &h_err, 1));
+    if (h_err) return ctx_fail(ctx, KOMBGPU_EINVAL, "a directed entry lies outside this rank's rows [%u, %u) or names a unitig >= %u", v_lo, v_lo + n_local, n_global);
     if (nd) KG_LAUNCH(ctx, part_cols_kernel, min(grid_for(nd, kThreads), 148u * 16u), kThreads, 0, uniq.p, nd, col.p);
     if (n_local)
         KG_LAUNCH(ctx, part_degree_kernel, min(grid_for(n_local, kThreads), 148u * 8u), kThreads, 0, row_ptr.p, n_local, deg.p,

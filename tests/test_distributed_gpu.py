@@ -103,3 +103,22 @@ def test_partition_kernels_world2(tmp_path, oracle_mod, case, peel_mode):
         assert parts[0]["stats"]["exchange_subrounds"] > 0
     else:
         assert parts[0]["stats"]["peel_mode"] == "gather"
+
+
+def test_part_build_rejects_misrouted_entries():
+    """A directed entry whose source is not one of the rank's rows, or whose target is not a unitig of the graph, is an
+    error (KOMBGPU_EINVAL), not a write past the rank's arrays."""
+    import torch
+    import komb_b200
+    from komb_b200.distributed import CudaEngine
+    ctx = komb_b200.Context(0)
+    eng = CudaEngine(ctx)
+    ok = torch.tensor([(10 << 32) | 3, (11 << 32) | 10, (19 << 32) | 0], dtype=torch.int64, device="cuda")
+    part = eng.build_part(ok, 10, 20, 30)
+    assert eng.part_counts(part) == {"n_local": 10, "n_directed": 3, "max_degree": 1}
+    eng.lib.kombgpu_part_destroy(part)
+    for bad in ((25 << 32) | 3, (9 << 32) | 3, (12 << 32) | 30):
+        entries = torch.tensor([(10 << 32) | 3, bad], dtype=torch.int64, device="cuda")
+        with pytest.raises(komb_b200.KombGpuError, match="outside this rank's rows"):
+            eng.build_part(entries, 10, 20, 30)
+    ctx.close()
