@@ -840,7 +840,12 @@ def run_ours_multi(args, rank, world, local_rank):
             line["configs"]["cfg3_strong"] = run_config_multi(ctx, comm, tcomm, "cfg3", world, rank, hbm_gbs, timed)
         except Exception as e:
             line["configs"]["cfg3_strong"] = {"error": f"{type(e).__name__}: {e}"}
-        for name in (["cfg4_eighth"] + (["cfg4"] if world == 8 else [])):
+        only = os.environ.get("KOMB_BENCH_ONLY_CONFIG")
+        if only:
+            line["configs"] = {}
+        for name in (["cfg4_eighth"] + (["cfg4", "cfg5"] if world == 8 else [])):
+            if only and name != only:
+                continue
             try:
                 line["configs"][name] = run_config_multi(ctx, comm, tcomm, name, world, rank, hbm_gbs, timed)
             except Exception as e:
@@ -865,6 +870,16 @@ def run_config_multi(ctx, comm, tcomm, name, world, rank, hbm_gbs, timed, reps: 
         a, b = rmat_device(26, 540_000_000 // world, n, 42 + 1000 * rank)
         kind, key_mode, verify = "pairs", komb_b200.KEY_EXACT64, True
         desc = f"cfg3: R-MAT scale 26, 540 M draws over 50 M unitigs (every rank draws 1/{world} of them), strong scaling"
+    elif name == "cfg5":
+        # the 1-GPU deep-core graph, every rank takes 1/world of its pair list (the generator is deterministic)
+        u, v, n = ramp_device(5000, 40, 9_800_000, 24, 40_000_000, 7)
+        lo, hi = u.numel() * rank // world, u.numel() * (rank + 1) // world
+        a, b = u[lo:hi].clone(), v[lo:hi].clone()
+        del u, v
+        torch.cuda.empty_cache()
+        kind, key_mode, verify = "pairs", komb_b200.KEY_EXACT64, True
+        desc = (f"cfg5: deep core: ramp of 5000 levels x 40 unitigs over an R-MAT background, 10 M unitigs, ids scrambled, "
+                f"{world} GPUs (strong scaling: every rank holds 1/{world} of the pair list)")
     else:
         scale = 8 if name == "cfg4_eighth" else 1
         n, pairs_total = 100_000_000 // scale, 500_000_000 // scale

@@ -206,9 +206,11 @@ struct EvTimer {   // CUDA-event split timer on the context's stream
 // against 14.7 ms).  Its walk is also the simpler, slower one per entry (a system-scope atomic and an owner lookup per
 // neighbour): cfg4 at full size, 243 M adjacency entries per rank and only 28 levels, takes it 42.9 ms against 23.9 ms;
 // a 1/8 share of cfg4 on 2 GPUs (122 M entries per rank) 22.1 against 15.0 ms; cfg2 (66 M per rank) 9.2 against 11.1 ms.
-// auto: asynchronous unless the largest degree of the graph exceeds kAsyncMaxDegree or a rank holds more than
-// kAsyncMaxEntries adjacency entries (the peel is then bound by the rate of decrements, not by the length of its chains).
+// auto: asynchronous unless the largest degree of the graph exceeds kAsyncMaxDegree, or a rank holds more than
+// kAsyncMaxEntries adjacency entries of a FLAT graph (largest degree <= kFlatDegree, hence few levels and short chains:
+// the peel is then bound by the rate of decrements, not by the length of its chains).
 constexpr int32_t kAsyncMaxDegree = 1 << 18;
+constexpr int32_t kFlatDegree = 1024;
 constexpr unsigned long long kAsyncMaxEntries = 96ull << 20;
 // A graph small enough for one GPU to peel in a few milliseconds is not partitioned for the peel at all (rpeel.cu): every
 // rank pulls the other ranks' rows and runs the single-GPU kernel (cfg2 x 2 / x 4: 4.4 / 10.9 ms against 9.3 / 18.6 ms).
@@ -386,7 +388,7 @@ int dist_build(kombgpu_comm *c, const uint32_t *a, const uint32_t *b, uint64_t c
             dir_total += all_shape[q * 2 + 1];
         }
         if (world > 1 && world <= kReplicateMaxWorld && dir_total <= kReplicateMaxEntries) choice = 2;
-        else choice = (gmax_now <= kAsyncMaxDegree && dir_max <= kAsyncMaxEntries) ? 1 : 0;
+        else choice = (gmax_now <= kAsyncMaxDegree && !(dir_max > kAsyncMaxEntries && gmax_now <= kFlatDegree)) ? 1 : 0;
     }
     const bool by_row = choice != 0;
     g->peel_choice = choice;
