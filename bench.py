@@ -843,9 +843,7 @@ def run_ours_multi(args, rank, world, local_rank):
         only = os.environ.get("KOMB_BENCH_ONLY_CONFIG")
         if only:
             line["configs"] = {}
-        for name in (["cfg4_eighth"] + (["cfg4", "cfg5"] if world == 8 else [])):
-            if only and name != only:
-                continue
+        for name in ([only] if only else ["cfg4_eighth"] + (["cfg4", "cfg5"] if world == 8 else [])):
             try:
                 line["configs"][name] = run_config_multi(ctx, comm, tcomm, name, world, rank, hbm_gbs, timed)
             except Exception as e:

@@ -37,7 +37,8 @@ namespace {
 constexpr int kAThreads = 512;
 constexpr int kAWarps = kAThreads / 32;
 constexpr int kAU = 4;                        // independent decrement chains per lane
-constexpr uint32_t kASlice = 2048;            // rows longer than this are cut into slices of this many entries
+constexpr uint32_t kASlice = 256;             // rows longer than this are cut into slices of this many entries (a slice is walked by one warp,
+                                              // 128 entries per round trip: cfg5 on 2 GPUs took 7.7 s with 2048-entry slices)
 constexpr int kAScanItems = 8;
 constexpr unsigned long long kAEmpty = ~0ull;
 constexpr unsigned long long kASliceFlag = 1ull << 63;   // entry = flag | piece << 32 | local id ; else k << 32 | local id
