@@ -2,6 +2,7 @@
 """bench.py — throughput of the KOMB hot path (hits -> graph -> k-core -> CORE-A).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-configs] [--no-cpu-baseline]
+    (KOMB_BENCH_ONLY_CONFIG=cfg3|cfg4_eighth|cfg4|cfg5 at N > 1: run the step and only that secondary config)
 
 One "step" = one pass of the whole hot path over one synthetic batch (BASELINE.json configs[1]: 1 M unitigs,
 5 M read pairs, ~20 M hits per GPU).  N = 1 runs the single-GPU path; N > 1 (launched with torch.distributed.run,
