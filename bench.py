@@ -837,13 +837,12 @@ def run_ours_multi(args, rank, world, local_rank):
     ctx.trim()
     if not args.no_configs:
         line["configs"] = {}
-        try:
-            line["configs"]["cfg3_strong"] = run_config_multi(ctx, comm, tcomm, "cfg3", world, rank, hbm_gbs, timed)
-        except Exception as e:
-            line["configs"]["cfg3_strong"] = {"error": f"{type(e).__name__}: {e}"}
         only = os.environ.get("KOMB_BENCH_ONLY_CONFIG")
-        if only:
-            line["configs"] = {}
+        if not only:
+            try:
+                line["configs"]["cfg3_strong"] = run_config_multi(ctx, comm, tcomm, "cfg3", world, rank, hbm_gbs, timed)
+            except Exception as e:
+                line["configs"]["cfg3_strong"] = {"error": f"{type(e).__name__}: {e}"}
         for name in ([only] if only else ["cfg4_eighth"] + (["cfg4", "cfg5"] if world == 8 else [])):
             try:
                 line["configs"][name] = run_config_multi(ctx, comm, tcomm, name, world, rank, hbm_gbs, timed)
