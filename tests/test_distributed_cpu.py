@@ -99,3 +99,73 @@ def test_single_rank_needs_no_process_group(oracle_mod):
     deg, core = oracle_mod.coreness(400, oracle_mod.simplify(u, v))
     assert np.array_equal(res.coreness, core) and np.array_equal(res.degree, deg)
     assert res.stats["exchange_subrounds"] == 0
+
+
+def test_async_peel_level_rule_model():
+    """A numpy model of the level rule of the asynchronous partitioned peel (komb_b200/csrc/apeel.cu): the next level is the
+    global minimum of per-rank LOWER BOUNDS -- the survivors' degrees as the last scan saw them and every degree a decrement
+    left above the level -- not of the true surviving degrees.  A unitig that died since can make the bound too low (the
+    level it names is then empty: a wasted scan), never too high (a level skipped: a wrong coreness).  The model peels
+    partitioned graphs level by level with that rule, decrements applied in an arbitrary (shuffled) order inside a
+    level, and must reproduce the oracle's coreness; it also checks bound <= true minimum at every level."""
+    from komb_b200 import synth
+    from oracle import oracle
+    rng = np.random.default_rng(4)
+    for seed, n, m, world in [(1, 400, 3000, 2), (2, 1500, 12000, 3), (3, 90, 300, 4)]:
+        u, v = synth.rmat_edges(11, m, n_vertices=n, seed=seed)
+        edges = oracle.simplify(u, v)
+        exp_deg, exp_core = oracle.coreness(n, edges)
+        eu, ev = oracle.unpack_edges(edges)
+        adj = [[] for _ in range(n)]
+        for a, b in zip(eu.tolist(), ev.tolist()):
+            adj[a].append(b); adj[b].append(a)
+        step = (n + world - 1) // world
+        owner = lambda x: x // step                                     # noqa: E731
+        deg = exp_deg.astype(np.int64).copy()
+        core = np.full(n, -1, np.int64)
+        alive = [list(range(q * step, min((q + 1) * step, n))) for q in range(world)]
+        bound = [min((deg[x] for x in alive[q]), default=None) for q in range(world)]   # before the first level: a pass
+        k_prev, empty_levels, levels = -1, 0, 0
+        while True:
+            lbs = [b for b in bound if b is not None]
+            if not lbs:
+                break
+            k = min(lbs)
+            assert k > k_prev
+            true_min = min((int(deg[x]) for q in range(world) for x in alive[q] if core[x] < 0), default=None)
+            assert true_min is None or k <= true_min                    # never above the true next level
+            k_prev = k
+            levels += 1
+            # scan: unitigs at degree k are pushed, survivors kept; the scan contributes the survivors' degrees to the bound
+            bound = [None] * world
+            pool = []
+            for q in range(world):
+                keep = []
+                for x in alive[q]:
+                    if core[x] >= 0 or deg[x] < k:
+                        continue                                         # peeled at an earlier level
+                    if deg[x] == k:
+                        pool.append(x)
+                    else:
+                        keep.append(x)
+                        bound[q] = int(deg[x]) if bound[q] is None else min(bound[q], int(deg[x]))
+                alive[q] = keep
+            if not pool:
+                empty_levels += 1
+            # the level: entries are taken in arbitrary order; a decrement that leaves old - 1 > k lowers the DECREMENTING
+            # rank's bound; the one that takes a degree from k + 1 to k pushes the unitig
+            while pool:
+                x = pool.pop(int(rng.integers(0, len(pool))))
+                assert core[x] < 0
+                core[x] = k
+                q = owner(x)
+                for y in adj[x]:
+                    old = int(deg[y])
+                    deg[y] = old - 1
+                    if old == k + 1:
+                        pool.append(y)
+                    elif old > k + 1:
+                        bound[q] = old - 1 if bound[q] is None else min(bound[q], old - 1)
+        assert np.array_equal(core, exp_core.astype(np.int64))
+        assert levels - empty_levels == len(set(exp_core.tolist()))      # every non-empty level was visited exactly once
+        assert empty_levels <= levels                                    # (stale bounds may add empty ones)
