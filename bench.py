@@ -581,8 +581,8 @@ def run_ours(args):
         "build_hits_per_s": H / (ms_build * 1e-3),
         "roofline": {"kernel": "peel_kernel (persistent cooperative frontier peel, warp-autonomous process phase)", "bound": "hbm",
                      "achieved": peel_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": peel_gbs / hbm_gbs,
-                     "traffic": 354.0e6, "traffic_source": "dram__bytes_read+write of one peel_kernel launch, ncu --set full "
-                     "(profiles/r1/r1x_peel_kernel_raw.csv; the 4 MB degree array stays in L2, so DRAM traffic is below "
+                     "traffic": 352.1e6, "traffic_source": "dram__bytes_read+write of one peel_kernel launch, ncu --set full "
+                     "(profiles/r2/r2ar_peel_kernel_raw.csv: 320.9 MB read + 31.2 MB written; the 4 MB degree array stays in L2, so DRAM traffic is below "
                      "the algorithmic bytes; the kernel is bound by its dependency depth and by L2 atomics, not by bytes)",
                      "algorithmic_bytes": b_peel, "kernel_ms": ms_peel_kernel, "peak_source": peak_src},
         "e2e": {"value": H / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": 8 * H, "d2h_bytes_per_step": int(d2h),
