@@ -169,3 +169,75 @@ def test_async_peel_level_rule_model():
         assert np.array_equal(core, exp_core.astype(np.int64))
         assert levels - empty_levels == len(set(exp_core.tolist()))      # every non-empty level was visited exactly once
         assert empty_levels <= levels                                    # (stale bounds may add empty ones)
+
+
+def test_async_peel_end_of_level_detection_model():
+    """A randomised interleaving model of the end-of-level test of the asynchronous partitioned peel (apeel.cu): every
+    rank counts entries pushed into its pool (tail: bumped by the PRODUCER, at the target, before the producer's own entry
+    counts as done) and entries processed (done).  A manager reads done then tail of every rank, then every tail once
+    more; equal and unchanged must imply that at some instant nobody had work.  The model interleaves worker steps and
+    the manager's individual reads at random and checks that the manager never declares the end while an entry is
+    queued or in flight -- and that it does declare it once everything is processed."""
+    rng = np.random.default_rng(12)
+    for trial in range(300):
+        world = int(rng.integers(2, 5))
+        tail = [0] * world; done = [0] * world; head = [0] * world
+        # initial frontier (the scan's pushes) and a budget of discoveries each processed entry may still make
+        for q in range(world):
+            tail[q] = int(rng.integers(0, 4))
+        budget = int(rng.integers(0, 40))
+        if sum(tail) == 0:
+            tail[0] = 1
+        in_flight = []            # entries taken by a worker: [rank, pushes still to make]
+        declared = False
+        reads = {}                # the manager's collect in progress
+        plan = []                 # remaining reads of the current collect: ("d", q), ("t", q), ("t2", q)
+        steps = 0
+        while not declared:
+            steps += 1
+            assert steps < 100000
+            work_left = any(head[q] < tail[q] for q in range(world)) or bool(in_flight)
+            choice = rng.random()
+            if work_left and choice < 0.6:
+                movable = [("take", q) for q in range(world) if head[q] < tail[q]] + [("step", i) for i in range(len(in_flight))]
+                kind, x = movable[int(rng.integers(0, len(movable)))]
+                if kind == "take":
+                    head[x] += 1
+                    pushes = int(rng.integers(0, 3)) if budget > 0 else 0
+                    budget -= pushes
+                    in_flight.append([x, pushes])
+                else:
+                    ent = in_flight[x]
+                    if ent[1] > 0:                      # a discovery: the TARGET's tail first ...
+                        tail[int(rng.integers(0, world))] += 1
+                        ent[1] -= 1
+                    else:                               # ... the entry's own done last
+                        done[ent[0]] += 1
+                        in_flight.pop(x)
+            else:
+                if not plan:                            # start a collect: all done reads, then all tail reads (any order inside)
+                    d_reads = [("d", q) for q in range(world)]; t_reads = [("t", q) for q in range(world)]
+                    rng.shuffle(d_reads); rng.shuffle(t_reads)
+                    # the two reads of ONE rank may be reordered by the hardware: model that by mixing the groups
+                    first = d_reads + t_reads
+                    if rng.random() < 0.5:
+                        rng.shuffle(first)
+                    second = [("t2", q) for q in range(world)]
+                    rng.shuffle(second)
+                    plan = first + ["check1"] + second + ["check2"]
+                    reads = {}
+                op = plan.pop(0)
+                if op == "check1":
+                    if any(reads[("d", q)] != reads[("t", q)] for q in range(world)):
+                        plan = []                        # somebody busy: start over
+                elif op == "check2":
+                    if all(reads[("t2", q)] == reads[("t", q)] for q in range(world)):
+                        # declared: there must be no work anywhere, now or (by stability) at the instant it refers to
+                        assert not any(head[q] < tail[q] for q in range(world)) and not in_flight, (trial, tail, done, head)
+                        assert done == tail
+                        declared = True
+                    plan = []
+                else:
+                    kind, q = op
+                    reads[op] = done[q] if kind == "d" else tail[q]
+        assert sum(done) == sum(tail)
