@@ -160,7 +160,8 @@ int kombgpu_graph_csr(const kombgpu_graph *g, uint64_t *row_ptr, uint32_t *col);
  * bytes of input f (host pointers; mate 1 first).  Numbering is deterministic, unlike the reference's (quirk Q4):
  * read ids follow first appearance; unitig ids follow @SQ header order, then first appearance, over unitigs with
  * at least one hit.  Strings are matched by their bytes, never by hash alone.  Empty lines and lines with fewer
- * than three tokens (undefined behaviour in the reference) fail with KOMBGPU_EINVAL.  The hits stay on the
+ * than three tokens (undefined behaviour in the reference) fail with KOMBGPU_EINVAL; so do more than 2^30 lines in
+ * one call.  The hits stay on the
  * device: kombgpu_build_graph_hits builds the graph from them without a host round trip. */
 typedef struct kombgpu_hits kombgpu_hits;
 int kombgpu_sam_parse(kombgpu_ctx *ctx, const char *const *texts, const uint64_t *sizes, int n_files, kombgpu_hits **out);

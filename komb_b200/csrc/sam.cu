@@ -413,7 +413,8 @@ int sam_parse(kombgpu_ctx *ctx, const char *const *texts, const uint64_t *sizes,
     std::vector<uint64_t> line_base(n_files, 0);
     for (int f = 0; f < n_files; ++f) { line_base[f] = n_lines; n_lines += n_lines_f[f + 1]; }
     h->n_lines = n_lines;
-    if (n_lines >= (1ull << 32)) return ctx_fail(ctx, KOMBGPU_EINVAL, "%llu lines exceed the 2^32 per-call limit", (unsigned long long)n_lines);
+    // the compaction scan carries two counters in one 64-bit sum (hits low, @SQ records high) next to two status bits
+    if (n_lines >= (1ull << 30)) return ctx_fail(ctx, KOMBGPU_EINVAL, "%llu lines exceed the 2^30 per-call limit", (unsigned long long)n_lines);
 
     DevBuf<uint8_t> kind;
     ItemBufs lkey, lname;   // per line
