@@ -113,3 +113,45 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.kombgpu_abi_version() == 1
     assert ctypes.sizeof(_lib.Stats) == 80   # sizeof(kombgpu_stats) on LP64
+
+
+def test_komb2_cli_and_no_cpu_fallback(tmp_path):
+    """The drop-in's command line (reference src/komb2.cpp:28-76, TCLAP semantics) needs no GPU; the analysis does, and
+    without one komb2 fails loudly (exit 1, message on stderr) -- for the device tokeniser and for the host one alike:
+    there is no CPU fallback."""
+    import os
+    komb2 = ROOT / "bin" / "komb2"
+    if not komb2.exists():
+        subprocess.run(["make", "-C", str(ROOT), "bin/komb2"], check=True, capture_output=True)
+    cp = subprocess.run([str(komb2), "--version"], capture_output=True, text=True)
+    assert cp.returncode == 0 and "version: 2.0" in cp.stdout
+    cp = subprocess.run([str(komb2), "-i", "x.sam"], capture_output=True, text=True)
+    assert cp.returncode == 1 and "Required argument" in cp.stderr
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible: the no-fallback half of this test is for CPU-only hosts")
+    except ImportError:
+        pass
+    (tmp_path / "r1.sam").write_bytes(b"r1/1\t0\tu1\t1\nr1/1\t0\tu2\t1\n")
+    (tmp_path / "r2.sam").write_bytes(b"r1/2\t0\tu3\t1\n")
+    (tmp_path / "u.fa").write_text(">u1\nACGT\n")
+    for mode in ("gpu", "host"):
+        cp = subprocess.run([str(komb2), "-t", "2", "-i", str(tmp_path / "r1.sam"), "-j", str(tmp_path / "r2.sam"), "-u", str(tmp_path / "u.fa"),
+                             "-o", str(tmp_path)], capture_output=True, text=True, env={**os.environ, "KOMB_TOKENIZE": mode})
+        assert cp.returncode == 1 and "cannot use CUDA device" in cp.stderr, (mode, cp.stderr)
+        assert not (tmp_path / "kcore.tsv").exists()
+
+
+def test_python_api_fails_loudly_without_a_gpu():
+    """komb_b200.Context raises KOMBGPU_ENODEV on a host without a usable B200: nothing in the package computes on the CPU."""
+    import komb_b200
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible")
+    except ImportError:
+        pass
+    with pytest.raises(komb_b200.KombGpuError) as e:
+        komb_b200.Context(0)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
